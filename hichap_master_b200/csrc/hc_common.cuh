@@ -1,0 +1,106 @@
+// Shared helpers for libhichap_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/hichap_b200.h"
+
+void hc_set_error(const char* fmt, ...);
+void hc_count_launch(int n = 1);
+
+#define HC_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            hc_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                 \
+                         cudaGetErrorString(e_));                                           \
+            return HC_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define HC_LAUNCH_CHECK()                                                                   \
+    do {                                                                                    \
+        hc_count_launch();                                                                  \
+        HC_CUDA(cudaGetLastError());                                                        \
+    } while (0)
+
+#define HC_REQUIRE(cond, msg)                                                               \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            hc_set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg);           \
+            return HC_ERR_ARG;                                                              \
+        }                                                                                   \
+    } while (0)
+
+static inline int hc_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;  // B200
+    }
+    return sms;
+}
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream_v4(const int32_t* p) {
+    // 128-bit streaming load: read-only path, do not allocate in L1 (data is touched once)
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void st_stream_v2f64(double* p, double a, double b) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of doubles in a fixed order (deterministic); red must hold >= 32 doubles.
+// Every thread receives the result.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect red from a previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum_ll(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+
+// Order-preserving map double -> uint64 (total order; NaNs sort high/low by sign bit).
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}

@@ -1,0 +1,412 @@
+// (c) Two-step allelic correction: matrixBuilding.py:984-1023 (TwoStepCorrection) with
+// Coverage_M :904-912, Gap_defined :915-929, Gap_definedLowRes :742-753, Trans2symmetry :945-979,
+// Trans2symmetryLowRes :770-776 and Correct_VC :780-790; also the building blocks of
+// GenomeWideMatrixCorrection :857-901.
+//
+// Data flow for one haplotype matrix X (int32, n x n):
+//   rowstats         : row sums + non-zero counts                      (reads X once)
+//   twostep_alpha    : O(n) on one CTA: coverage -> gap rows, alpha, percentiles (radix select)
+//   sym pass ROWSUM  : tile pairs (I,J)/(J,I): S = X/alpha[:,None]; Sym = f(S_ij, S_ji, gap);
+//                      deterministic per-tile partial row sums          (reads X once)
+//   vc_scale         : s = rowsum(Sym)^(2/3), 0 -> 1
+//   sym pass TOTAL   : sum_ij Sym_ij / (s_i s_j)                        (reads X once)
+//   sym pass WRITE   : out = RF * Sym_ij / (s_j s_i), RF = mean(X)/mean(Cor)  (reads X, writes fp64)
+// The reference's 2*N^2 interpreted iterations in Trans2symmetry become the tile-pair passes.
+// Roofline: HBM-bound, (4+4+4+4+8) N^2 = 24 N^2 bytes per haplotype matrix (+4 N^2 for TM).
+#include <math.h>
+#include "hc_common.cuh"
+#include "hc_select.cuh"
+
+namespace {
+
+constexpr int T = 64;          // tile side
+constexpr int LDB = T + 1;     // padded leading dimension of the transposed-access tile
+constexpr int TS_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const int32_t* __restrict__ M, int64_t ld, int nrows, int ncols, int vec_ok,
+                int64_t* __restrict__ rowsum, int32_t* __restrict__ rownnz) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const int32_t* row = M + (int64_t)r * ld;
+    long long s = 0;
+    int c = 0;
+    int done = 0;
+    if (vec_ok) {
+        const int nvec = ncols >> 2;
+        for (int v = lane; v < nvec; v += 32) {
+            const int4 a = ld_stream_v4(row + 4 * v);
+            s += (long long)a.x + a.y + a.z + a.w;
+            c += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+        }
+        done = nvec << 2;
+    }
+    for (int j = done + lane; j < ncols; j += 32) { const int x = row[j]; s += x; c += (x != 0); }
+    s = warp_sum_ll(s);
+    c = warp_sum_i(c);
+    if (lane == 0) { rowsum[r] = s; if (rownnz) rownnz[r] = c; }
+}
+
+// ---------------------------------------------------------------------------------------
+struct AlphaArgs {
+    const int64_t* rs_t; const int64_t* rs_m; const int64_t* rs_p;
+    const int32_t* nnz_a; const int32_t* nnz_b;
+    int n; int ncols; int gap_mode;
+    double* alpha; uint8_t* gf_a; uint8_t* gf_b; int32_t* gi_a; int32_t* gi_b; int32_t* ngap;
+    double* work;
+    double q25, q20;
+};
+
+__device__ void gap_rows(const int32_t* nnz, int n, int ncols, int gap_mode, double q25, double* cov,
+                         uint8_t* gf, HcSelectSmem* sm) {
+    long long cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        // 1 - zeros/len, in the reference's operation order (matrixBuilding.py:909)
+        const double v = __dadd_rn(1.0, -__ddiv_rn((double)(ncols - nnz[i]), (double)ncols));
+        cov[i] = v;
+        cnt += (v != 0.0);
+    }
+    __syncthreads();
+    double thr = 0.1;
+    if (gap_mode == HC_GAP_PERCENTILE) {
+        cnt = block_sum_ll(cnt, sm->redll);
+        thr = block_percentile([&](long long i) { return cov[i]; }, [&](long long i) { return cov[i] != 0.0; },
+                               n, cnt, q25, sm);
+        if (thr > 0.2) thr = 0.2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gf[i] = cov[i] < thr;
+    __syncthreads();
+}
+
+// ordered compaction of flagged indices by one CTA
+__device__ void compact_flags(const uint8_t* gf, int n, int32_t* idx, int32_t* count) {
+    __shared__ int wtot[32];
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b0 = 0; b0 < n; b0 += blockDim.x) {
+        const int i = b0 + threadIdx.x;
+        const bool f = i < n && gf[i];
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wtot[wid] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; ++w) off += wtot[w];
+        if (f) idx[off + __popc(m & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nw; ++w) t += wtot[w]; base_s += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base_s;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) twostep_alpha_kernel(AlphaArgs a) {
+    __shared__ HcSelectSmem sm;
+    const int n = a.n;
+    double* cov_a = a.work;
+    double* cov_b = a.work + n;
+    gap_rows(a.nnz_a, n, a.ncols, a.gap_mode, a.q25, cov_a, a.gf_a, &sm);
+    compact_flags(a.gf_a, n, a.gi_a, a.ngap);
+    const bool two = a.nnz_b != nullptr;
+    if (two) {
+        gap_rows(a.nnz_b, n, a.ncols, a.gap_mode, a.q25, cov_b, a.gf_b, &sm);
+        compact_flags(a.gf_b, n, a.gi_b, a.ngap + 1);
+    }
+    // non-gap rows: NonGap(A) | NonGap(B)  ==  not (gap_a and gap_b)      (matrixBuilding.py:999)
+    auto nongap = [&](long long i) { return two ? !(a.gf_a[i] && a.gf_b[i]) : !a.gf_a[i]; };
+    double* al = a.alpha;
+    double mx = -INFINITY;
+    long long cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = __ddiv_rn((double)(a.rs_m[i] + a.rs_p[i]), (double)(a.rs_t[i] + 1));
+        al[i] = v;
+        if (nongap(i)) { mx = fmax(mx, v); ++cnt; }
+    }
+    cnt = block_sum_ll(cnt, sm.redll);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = sm.red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, sm.red[w]);
+    __syncthreads();
+    if (cnt == 0) mx = __longlong_as_double(0x7ff8000000000000ll);  // np.max of an empty selection has no value
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = __ddiv_rn(al[i], mx);
+        if (v == 0.0) v = 1.0;
+        al[i] = v;
+    }
+    __syncthreads();
+    const double thr = block_percentile([&](long long i) { return al[i]; }, nongap, n, cnt, a.q20, &sm);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) if (al[i] < thr) al[i] = thr;
+}
+
+// ---------------------------------------------------------------------------------------
+// tile-pair passes
+// ---------------------------------------------------------------------------------------
+enum { PASS_ROWSUM = 0, PASS_TOTAL = 1, PASS_WRITE = 2 };
+
+struct SymArgs {
+    const int32_t* X; int64_t ld; int n; int nT;
+    const double* alpha; const uint8_t* gapflag; int has_gap;
+    double* ra;           // [nT*T] 1 / alpha_i (0 beyond n)
+    double* partial;      // [nT][nT*T] per-tile partial row sums of Sym
+    double* rs;           // [nT*T] 1 / s_i  (s = rowsum^(2/3), 0 -> 1)
+    double* cta_partial;  // [npairs]
+    const double* scalars; // scalars[0] = RF
+    double* out; int64_t ld_out;
+};
+
+__device__ __forceinline__ void tile_index(int idx, int nT, int* I, int* J) {
+    // row-major enumeration of the upper triangle (I <= J)
+    int i = (int)floor(((2.0 * nT + 1.0) - sqrt((2.0 * nT + 1.0) * (2.0 * nT + 1.0) - 8.0 * idx)) * 0.5);
+    if (i < 0) i = 0;
+    while (i > 0 && (long long)i * (2 * nT - i + 1) / 2 > idx) --i;
+    while ((long long)(i + 1) * (2 * nT - i) / 2 <= idx) ++i;
+    *I = i;
+    *J = i + (idx - (int)((long long)i * (2 * nT - i + 1) / 2));
+}
+
+__device__ __forceinline__ void load_tile(const int32_t* __restrict__ X, int64_t ld, int n, int r0, int c0,
+                                          int32_t* dst, int ldd) {
+    // 64 rows x 16 int4; thread t loads (row = t/16 + 16a, vec = t%16)
+    const int v = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = rr + 16 * a, gi = r0 + r, gc = c0 + 4 * v;
+        int4 x = make_int4(0, 0, 0, 0);
+        if (gi < n && gc < (int)ld) x = ld_stream_v4(X + (int64_t)gi * ld + gc);
+        int32_t* d = dst + r * ldd + 4 * v;
+        d[0] = gc < n ? x.x : 0; d[1] = gc + 1 < n ? x.y : 0; d[2] = gc + 2 < n ? x.z : 0; d[3] = gc + 3 < n ? x.w : 0;
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* sA = reinterpret_cast<int32_t*>(smem_raw);     // [T][T]    tile (I,J)
+    int32_t* sB = sA + T * T;                               // [T][LDB]  tile (J,I)
+    double* sV = reinterpret_cast<double*>(sB + T * LDB);  // PASS_WRITE: [T][LDB] staged mirror tile
+    __shared__ double colred[8][T];
+    __shared__ double red[32];
+
+    int I, J;
+    tile_index(blockIdx.x, a.nT, &I, &J);
+    const int r0 = I * T, c0 = J * T;
+    load_tile(a.X, a.ld, a.n, r0, c0, sA, T);
+    if (I != J) load_tile(a.X, a.ld, a.n, c0, r0, sB, LDB);
+    __syncthreads();
+    const int32_t* tB = (I != J) ? sB : sA;
+    const int ldb = (I != J) ? LDB : T;
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps; warp = one tile row at a time
+    double val[8][2];
+    double rowp[8];
+    double colp[2] = {0.0, 0.0};
+    double tot = 0.0;
+#pragma unroll
+    for (int ai = 0; ai < 8; ++ai) {
+        const int r = ty + 8 * ai, gi = r0 + r;
+        const bool vi = gi < a.n;
+        const double ra_i = a.ra[gi];
+        const bool g_i = a.has_gap && vi && a.gapflag[gi];
+        const double rs_i = (PASS != PASS_ROWSUM && vi) ? a.rs[gi] : 0.0;
+        double rsum = 0.0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int c = tx + 32 * b, gj = c0 + c;
+            const bool vj = gj < a.n;
+            const double ra_j = a.ra[gj];
+            const double sij = (double)sA[r * T + c] * ra_i;
+            const double sji = (double)tB[c * ldb + r] * ra_j;
+            double sym;
+            if (gi == gj) sym = sij;
+            else if (!a.has_gap) sym = sij + sji;
+            else if (g_i && a.gapflag[vj ? gj : 0]) sym = fmax(sij, sji);
+            else sym = (sij + sji) * 0.5;
+            if (!(vi && vj)) sym = 0.0;
+            if (PASS == PASS_ROWSUM) { rsum += sym; colp[b] += sym; }
+            else {
+                const double cor = sym * (rs_i * (vj ? a.rs[gj] : 0.0));
+                if (PASS == PASS_TOTAL) tot += cor; else val[ai][b] = cor;
+            }
+        }
+        rowp[ai] = rsum;
+    }
+
+    if (PASS == PASS_ROWSUM) {
+        const int64_t np = (int64_t)a.nT * T;
+#pragma unroll
+        for (int ai = 0; ai < 8; ++ai) {
+            const double s = warp_sum(rowp[ai]);
+            if (tx == 0) a.partial[(int64_t)J * np + r0 + ty + 8 * ai] = s;   // rows of block I, other block J
+        }
+        if (I != J) {
+            colred[ty][tx] = colp[0]; colred[ty][tx + 32] = colp[1];
+            __syncthreads();
+            if (threadIdx.x < T) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += colred[w][threadIdx.x];
+                a.partial[(int64_t)I * np + c0 + threadIdx.x] = s;           // rows of block J, other block I
+            }
+        }
+    } else if (PASS == PASS_TOTAL) {
+        const double s = block_sum(tot, red);
+        if (threadIdx.x == 0) a.cta_partial[blockIdx.x] = (I != J) ? 2.0 * s : s;
+    } else {
+        const double rf = a.scalars[0];
+#pragma unroll
+        for (int ai = 0; ai < 8; ++ai) {
+            const int r = ty + 8 * ai, gi = r0 + r;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int c = tx + 32 * b, gj = c0 + c;
+                const double v = rf * val[ai][b];
+                if (gi < a.n && gj < a.n) a.out[(int64_t)gi * a.ld_out + gj] = v;
+                if (I != J) sV[c * LDB + r] = v;
+            }
+        }
+        if (I != J) {
+            __syncthreads();
+#pragma unroll
+            for (int ai = 0; ai < 8; ++ai) {
+                const int c = ty + 8 * ai, gj = c0 + c;   // row of the mirrored tile
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int r = tx + 32 * b, gi = r0 + r;
+                    if (gi < a.n && gj < a.n) a.out[(int64_t)gj * a.ld_out + gi] = sV[c * LDB + r];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) recip_alpha_kernel(SymArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.nT * T) a.ra[i] = i < a.n ? 1.0 / a.alpha[i] : 0.0;
+}
+
+// s_i = (sum_K partial[K][i])^(2/3), zeros -> 1; store the reciprocal
+__global__ void __launch_bounds__(256) vc_scale_kernel(SymArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t np = (int64_t)a.nT * T;
+    if (i >= np) return;
+    double s = 0.0;
+    if (i < a.n) for (int K = 0; K < a.nT; ++K) s += a.partial[(int64_t)K * np + i];
+    s = pow(s, 2.0 / 3.0);
+    if (s == 0.0) s = 1.0;
+    a.rs[i] = 1.0 / s;
+}
+
+// RF = mean(X) / mean(Cor)
+__global__ void __launch_bounds__(1024)
+vc_rescale_factor_kernel(const double* __restrict__ cta_partial, int npairs, const int64_t* __restrict__ rowsum_x,
+                         int n, double* __restrict__ scalars) {
+    __shared__ double red[32];
+    __shared__ long long redll[32];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < npairs; i += blockDim.x) t += cta_partial[i];
+    t = block_sum(t, red);
+    long long sx = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sx += rowsum_x[i];
+    sx = block_sum_ll(sx, redll);
+    if (threadIdx.x == 0) {
+        const double cells = (double)n * (double)n;
+        const double mean_x = (double)sx / cells, mean_cor = t / cells;
+        scalars[0] = mean_x / mean_cor;
+        scalars[1] = mean_x;
+        scalars[2] = mean_cor;
+    }
+}
+
+struct TwoStepWork { double* partial; double* rs; double* ra; double* cta_partial; double* scalars; };
+
+TwoStepWork carve(void* work, int n) {
+    const int64_t nT = (n + T - 1) / T, np = nT * T, npairs = nT * (nT + 1) / 2;
+    TwoStepWork w;
+    w.partial = reinterpret_cast<double*>(work);
+    w.rs = w.partial + nT * np;
+    w.ra = w.rs + np;
+    w.cta_partial = w.ra + np;
+    w.scalars = w.cta_partial + npairs;
+    return w;
+}
+
+}  // namespace
+
+extern "C" int hc_rowstats_i32(const int32_t* M, int64_t ld, int32_t nrows, int32_t ncols, int64_t* rowsum,
+                               int32_t* rownnz, void* stream) {
+    HC_REQUIRE(nrows >= 0 && ncols >= 0 && ld >= ncols, "shape");
+    if (nrows == 0) return HC_OK;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(M) & 15u) == 0) && ((ld & 3) == 0);
+    const int blocks = (int)(((int64_t)nrows * 32 + 255) / 256);
+    rowstats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(M, ld, nrows, ncols, vec_ok, rowsum, rownnz);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int hc_twostep_alpha(const int64_t* rowsum_t, const int64_t* rowsum_m, const int64_t* rowsum_p,
+                                const int32_t* nnz_a, const int32_t* nnz_b, int32_t n, int32_t ncols,
+                                int32_t gap_mode, double* alpha, uint8_t* gapflag_a, uint8_t* gapflag_b,
+                                int32_t* gapidx_a, int32_t* gapidx_b, int32_t* ngap, double* work, void* stream) {
+    HC_REQUIRE(n > 0 && ncols > 0, "n>0, ncols>0");
+    HC_REQUIRE(gap_mode == HC_GAP_PERCENTILE || gap_mode == HC_GAP_FIXED, "gap_mode");
+    HC_REQUIRE(nnz_a && gapflag_a && gapidx_a && ngap && alpha && work, "null pointer");
+    HC_REQUIRE(nnz_b == nullptr || (gapflag_b && gapidx_b), "second gap outputs");
+    AlphaArgs a;
+    a.rs_t = rowsum_t; a.rs_m = rowsum_m; a.rs_p = rowsum_p; a.nnz_a = nnz_a; a.nnz_b = nnz_b;
+    a.n = n; a.ncols = ncols; a.gap_mode = gap_mode;
+    a.alpha = alpha; a.gf_a = gapflag_a; a.gf_b = gapflag_b; a.gi_a = gapidx_a; a.gi_b = gapidx_b; a.ngap = ngap;
+    a.work = work;
+    a.q25 = 25.0 / 100.0;  // np.percentile divides q by 100 first
+    a.q20 = 20.0 / 100.0;
+    twostep_alpha_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int64_t hc_twostep_work_bytes(int32_t n) {
+    const int64_t nT = (n + T - 1) / T, np = nT * T, npairs = nT * (nT + 1) / 2;
+    return (int64_t)sizeof(double) * (nT * np + 2 * np + npairs + 8);
+}
+
+extern "C" int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const double* alpha,
+                                  const uint8_t* gapflag, int32_t has_gap, const int64_t* rowsum_x, double* out,
+                                  int64_t ld_out, void* work, void* stream) {
+    HC_REQUIRE(n > 0 && ld >= n && (ld & 3) == 0 && ld_out >= n, "shape (ld multiple of 4)");
+    HC_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15u) == 0, "X must be 16-byte aligned");
+    HC_REQUIRE(!has_gap || gapflag != nullptr, "gapflag required when has_gap");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nT = (n + T - 1) / T;
+    const int64_t npairs64 = (int64_t)nT * (nT + 1) / 2;
+    HC_REQUIRE(npairs64 < (1ll << 31), "matrix too large");
+    const int npairs = (int)npairs64;
+    TwoStepWork w = carve(work, n);
+    SymArgs a;
+    a.X = X; a.ld = ld; a.n = n; a.nT = nT; a.alpha = alpha; a.gapflag = gapflag; a.has_gap = has_gap ? 1 : 0;
+    a.partial = w.partial; a.rs = w.rs; a.ra = w.ra; a.cta_partial = w.cta_partial; a.scalars = w.scalars;
+    a.out = out; a.ld_out = ld_out;
+    const size_t smem_tiles = (size_t)(T * T + T * LDB) * sizeof(int32_t);
+    const size_t smem_write = smem_tiles + (size_t)T * LDB * sizeof(double);
+    HC_CUDA(cudaFuncSetAttribute(sym_pass_kernel<PASS_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    recip_alpha_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    sym_pass_kernel<PASS_ROWSUM><<<npairs, TS_THREADS, smem_tiles, s>>>(a);
+    HC_LAUNCH_CHECK();
+    vc_scale_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    sym_pass_kernel<PASS_TOTAL><<<npairs, TS_THREADS, smem_tiles, s>>>(a);
+    HC_LAUNCH_CHECK();
+    vc_rescale_factor_kernel<<<1, 1024, 0, s>>>(w.cta_partial, npairs, rowsum_x, n, w.scalars);
+    HC_LAUNCH_CHECK();
+    sym_pass_kernel<PASS_WRITE><<<npairs, TS_THREADS, smem_write, s>>>(a);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}

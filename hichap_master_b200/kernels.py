@@ -1,0 +1,184 @@
+"""Thin Python wrappers over the C ABI (one function per kernel family).  Everything here
+takes / returns device-resident objects from ``device.py``; the reference-named, NumPy-in /
+NumPy-out functions live in ``matrixBuilding.py`` and are built from these.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import IceParams, IceResult, IceRunInfo, check, lib
+from .device import DenseBatch, PairColumns, ptr, stream_ptr
+
+S_DTYPE = np.dtype([("bin1", "<i8"), ("bin2", "<i8"), ("IF", "<f8")])  # matrixBuilding.py:460-461
+
+
+# --------------------------------------------------------------------------------------
+# (a) binning
+# --------------------------------------------------------------------------------------
+def _oob_counter(dev):
+    return torch.zeros(1, dtype=torch.int64, device=dev)
+
+
+def _raise_oob(oob, what):
+    n = int(oob.item())
+    if n:
+        # the reference indexes a NumPy matrix with the bin and raises IndexError
+        raise IndexError("%d pair(s) fall outside the %s matrix (position beyond the chromosome "
+                         "length in the genomeSize file)" % (n, what))
+
+
+def bin_pairs_local(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
+                    check_bounds=True):
+    """Accumulate cis pairs into the per-chromosome matrices of ``batch`` (matrix i <->
+    chromosome index i).  matrixBuilding.py:595-603 and the allelic variants."""
+    oob = _oob_counter(batch.device)
+    check(lib().hc_bin_pairs_local(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
+                                   ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(batch.buf),
+                                   ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld),
+                                   len(batch), ptr(oob), stream_ptr()), "hc_bin_pairs_local")
+    if check_bounds:
+        _raise_oob(oob, "intra-chromosomal")
+
+
+def bin_pairs_whole(pairs: PairColumns, res: int, start1, start2, whole: DenseBatch,
+                    mode=_abi.HC_BIN_SYM_ALL, check_bounds=True):
+    """Accumulate pairs into the single genome-wide matrix ``whole`` (a 1-matrix batch) with
+    per-side chromosome start tables (device int64).  matrixBuilding.py:582-592."""
+    assert len(whole) == 1
+    oob = _oob_counter(whole.device)
+    check(lib().hc_bin_pairs_whole(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
+                                   ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(start1),
+                                   ptr(start2), int(start1.numel()), ptr(whole.buf), whole.sizes[0],
+                                   whole.lds[0], ptr(oob), stream_ptr()), "hc_bin_pairs_whole")
+    if check_bounds:
+        _raise_oob(oob, "genome-wide")
+
+
+def dense_nonzero_records(base_ptr: int, ld: int, nrows: int, ncols: int, triu: bool, is_f64: bool,
+                          device) -> np.ndarray:
+    """np.triu/np.nonzero marshalling (matrixBuilding.py:489-503, :515-521) on the device;
+    returns the reference's structured array (bin1, bin2, IF) in row-major order."""
+    row_ptr = torch.empty(nrows + 1, dtype=torch.int64, device=device)
+    check(lib().hc_dense_nonzero_count(C.c_void_p(base_ptr), ld, nrows, ncols, int(triu), int(is_f64),
+                                       ptr(row_ptr), stream_ptr()), "hc_dense_nonzero_count")
+    nnz = int(row_ptr[-1].item())
+    rec = np.zeros(nnz, dtype=S_DTYPE)
+    if nnz == 0:
+        return rec
+    b1 = torch.empty(nnz, dtype=torch.int32, device=device)
+    b2 = torch.empty(nnz, dtype=torch.int32, device=device)
+    val = torch.empty(nnz, dtype=torch.float64 if is_f64 else torch.int32, device=device)
+    check(lib().hc_dense_nonzero_extract(C.c_void_p(base_ptr), ld, nrows, ncols, int(triu), int(is_f64),
+                                         ptr(row_ptr), ptr(b1), ptr(b2), ptr(val), stream_ptr()),
+          "hc_dense_nonzero_extract")
+    rec["bin1"], rec["bin2"], rec["IF"] = b1.cpu().numpy(), b2.cpu().numpy(), val.cpu().numpy()
+    return rec
+
+
+# --------------------------------------------------------------------------------------
+# (b) ICE
+# --------------------------------------------------------------------------------------
+def ice_params(ignore_diags=1, mad_max=5, min_nnz=10, min_count=0, tol=1e-5, max_iters=200,
+               rescale_marginals=True, poll_every=8) -> IceParams:
+    return IceParams(float(tol), float(mad_max), int(min_nnz), int(min_count), int(ignore_diags),
+                     int(max_iters), int(bool(rescale_marginals)), int(poll_every))
+
+
+def ice_dense_filters(batch: DenseBatch, params: IceParams, chrom_off=None):
+    """Pre-iteration bin filters of ``cooler balance`` -> initial bias (device float64)."""
+    dev, n = batch.device, batch.nbins
+    nnz_marg = torch.empty(n, dtype=torch.float64, device=dev)
+    marg = torch.empty(n, dtype=torch.float64, device=dev)
+    check(lib().hc_ice_dense_marginals(ptr(batch.buf), ptr(batch.mat_off), ptr(batch.mat_n),
+                                       ptr(batch.mat_ld), ptr(batch.bin_off), len(batch),
+                                       params.ignore_diags, ptr(nnz_marg), ptr(marg), stream_ptr()),
+          "hc_ice_dense_marginals")
+    if chrom_off is None:
+        chrom_off = batch.bin_off
+    bias = torch.empty(n, dtype=torch.float64, device=dev)
+    work = torch.empty(2 * max(n, 1), dtype=torch.float64, device=dev)
+    check(lib().hc_ice_filter_bins(ptr(nnz_marg), ptr(marg), n, ptr(chrom_off), int(chrom_off.numel()) - 1,
+                                   C.byref(params), ptr(bias), ptr(work), stream_ptr()),
+          "hc_ice_filter_bins")
+    return bias
+
+
+def ice_dense_iterate(batch: DenseBatch, bias, params: IceParams):
+    """Run every problem of the batch to convergence on the device; ``bias`` is updated in
+    place to the final weights.  Returns (results ndarray of IceResult fields, IceRunInfo)."""
+    dev, n = batch.device, batch.nbins
+    work = torch.empty(3 * max(n, 1), dtype=torch.float64, device=dev)
+    res = torch.zeros(len(batch) * C.sizeof(IceResult), dtype=torch.uint8, device=dev)
+    info = IceRunInfo(0, 0.0)
+    check(lib().hc_ice_dense_balance(ptr(batch.buf), ptr(batch.mat_off), ptr(batch.mat_n),
+                                     ptr(batch.mat_ld), ptr(batch.bin_off), len(batch), batch.h_mat_n,
+                                     C.byref(params), ptr(bias), ptr(work), ptr(res), C.byref(info),
+                                     stream_ptr()), "hc_ice_dense_balance")
+    rdt = np.dtype([("scale", "<f8"), ("var", "<f8"), ("iters", "<i4"), ("converged", "<i4")])
+    return res.cpu().numpy().view(rdt), info
+
+
+def ice_balance_dense(batch: DenseBatch, chrom_off=None, **kw):
+    """``cooler balance --ignore-diags K --cis-only`` for a batch of intra-chromosomal
+    matrices (one independent problem per matrix), or genome-wide balancing for a 1-matrix
+    batch with ``chrom_off`` giving the chromosome boundaries used by the MAD-max filter.
+    Returns (weights float64 ndarray over the concatenated bins, stats dict)."""
+    params = ice_params(**kw)
+    bias = ice_dense_filters(batch, params, chrom_off)
+    results, info = ice_dense_iterate(batch, bias, params)
+    w = bias.cpu().numpy()
+    cis = len(batch) > 1 or chrom_off is None
+    stats = dict(tol=params.tol, min_nnz=params.min_nnz, min_count=params.min_count,
+                 mad_max=params.mad_max, cis_only=cis, ignore_diags=params.ignore_diags,
+                 divisive_weights=False, launches=int(info.launches), loop_ms=float(info.loop_ms))
+    if len(batch) == 1 and chrom_off is not None:
+        stats.update(scale=float(results["scale"][0]), var=float(results["var"][0]),
+                     converged=bool(results["converged"][0]), iters=int(results["iters"][0]))
+    else:
+        stats.update(scale=results["scale"].copy(), var=float(results["var"][-1]),
+                     converged=bool(results["var"][-1] < params.tol),
+                     iters=[int(i) for i in results["iters"]],
+                     converged_per_chrom=[bool(c) for c in results["converged"]])
+    return w, stats
+
+
+# --------------------------------------------------------------------------------------
+# (c) two-step allelic correction
+# --------------------------------------------------------------------------------------
+def rowstats(base_ptr: int, ld: int, nrows: int, ncols: int, device, want_nnz=True):
+    rs = torch.empty(nrows, dtype=torch.int64, device=device)
+    nz = torch.empty(nrows, dtype=torch.int32, device=device) if want_nnz else None
+    check(lib().hc_rowstats_i32(C.c_void_p(base_ptr), ld, nrows, ncols, ptr(rs), ptr(nz), stream_ptr()),
+          "hc_rowstats_i32")
+    return rs, nz
+
+
+def twostep_alpha(rs_t, rs_m, rs_p, nnz_a, nnz_b, n, ncols, gap_mode, device):
+    alpha = torch.empty(n, dtype=torch.float64, device=device)
+    gf_a = torch.empty(n, dtype=torch.uint8, device=device)
+    gi_a = torch.empty(n, dtype=torch.int32, device=device)
+    gf_b = torch.empty(n, dtype=torch.uint8, device=device) if nnz_b is not None else None
+    gi_b = torch.empty(n, dtype=torch.int32, device=device) if nnz_b is not None else None
+    ngap = torch.zeros(2, dtype=torch.int32, device=device)
+    work = torch.empty(2 * n, dtype=torch.float64, device=device)
+    check(lib().hc_twostep_alpha(ptr(rs_t), ptr(rs_m), ptr(rs_p), ptr(nnz_a), ptr(nnz_b), n, ncols,
+                                 gap_mode, ptr(alpha), ptr(gf_a), ptr(gf_b), ptr(gi_a), ptr(gi_b),
+                                 ptr(ngap), ptr(work), stream_ptr()), "hc_twostep_alpha")
+    return alpha, (gf_a, gi_a), (gf_b, gi_b), ngap
+
+
+def twostep_correct(x_ptr: int, ld: int, n: int, alpha, gapflag, has_gap: bool, rowsum_x, device,
+                    out=None):
+    """X/alpha -> Trans2symmetry -> Correct_VC(2/3) -> rescale, fused; returns an (n, n)
+    float64 device tensor."""
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device=device)
+    work = torch.empty(int(lib().hc_twostep_work_bytes(n)), dtype=torch.uint8, device=device)
+    check(lib().hc_twostep_correct(C.c_void_p(x_ptr), ld, n, ptr(alpha), ptr(gapflag), int(has_gap),
+                                   ptr(rowsum_x), ptr(out), out.stride(0), ptr(work), stream_ptr()),
+          "hc_twostep_correct")
+    return out

@@ -1,0 +1,292 @@
+"""B200 drop-in for the numeric functions of ``HiCHap/matrixBuilding.py`` (the ``matrix`` stage).
+
+Same callables, argument order and return layouts as the reference; the arithmetic runs in
+hand-written sm_100a kernels behind the C ABI (``include/hichap_b200.h``).  Citations are
+``file:line`` in the reference tree.
+
+Besides the reference's NumPy-in / NumPy-out signatures, every heavy function accepts the
+device-resident objects of ``device.py`` so a pipeline can keep matrices in HBM between the
+binning, ICE and correction kernels (``bin_traditional`` -> ``ice_balance_dense`` ->
+``two_step_device``).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from . import _abi, kernels
+from .device import DenseBatch, PairColumns, require_cuda
+from .pairs import chrom_passes, read_pairs
+
+log = logging.getLogger(__name__)
+
+S_dtype = kernels.S_DTYPE
+
+
+# ======================================================================================
+# genome / bin tables (host; matrixBuilding.py:349-454)
+# ======================================================================================
+def Load_Genome(genomeSize, chroms):
+    """matrixBuilding.py:349-366 -- ``{chrom: length}`` for chromosomes passing the filter.
+    ``lstrip('chr')`` strips the character set {c,h,r}, exactly as the reference does."""
+    genome = {}
+    with open(genomeSize, "r") as fh:
+        for line in fh:
+            parts = line.strip().split()
+            c = parts[0].lstrip("chr")
+            if chrom_passes(c, chroms):
+                genome[c] = int(parts[1])
+    return genome
+
+
+def Load_HaplotypeGenome(genomeSize, chroms):
+    """matrixBuilding.py:369-386."""
+    genome = {}
+    for c, l in Load_Genome(genomeSize, chroms).items():
+        genome["M" + c] = l
+        genome["P" + c] = l
+    return genome
+
+
+def Sort_Chromosomes(chro_lst):
+    """matrixBuilding.py:388-406 -- numeric labels ascending, then the others sorted."""
+    num, other = [], []
+    for name in chro_lst:
+        name = name.lstrip("chr")
+        try:
+            num.append(int(name))
+        except ValueError:
+            other.append(name)
+    return [str(v) for v in sorted(num)] + sorted(other)
+
+
+def _bins_from_genome(genome, Resolution, order):
+    table, nxt = {}, 0
+    for key, c in order:
+        span = genome[c] // Resolution
+        table[key] = (nxt, nxt + span)      # inclusive end, matrixBuilding.py:420-422
+        nxt += span + 1
+    return table, nxt
+
+
+def Get_Chro_Bins(genomeSize, Resolution, chroms):
+    """matrixBuilding.py:409-426 -- ({chrom: (start, end_inclusive)}, total bins)."""
+    genome = Load_Genome(genomeSize, chroms)
+    return _bins_from_genome(genome, Resolution, [(c, c) for c in Sort_Chromosomes(genome)])
+
+
+def Get_Chro_Bins_Haplotypes(genomeSize, Resolution, chroms):
+    """matrixBuilding.py:429-454 -- maternal chromosomes first, then paternal."""
+    genome = Load_Genome(genomeSize, chroms)
+    order = Sort_Chromosomes(genome)
+    return _bins_from_genome(genome, Resolution,
+                             [("M" + c, c) for c in order] + [("P" + c, c) for c in order])
+
+
+# ======================================================================================
+# (a) binning
+# ======================================================================================
+def _start_table(bins, keys, device):
+    return torch.tensor([bins[k][0] for k in keys], dtype=torch.int64, device=device)
+
+
+def _to_pair_columns(bed_IO, order, chroms, layout, device):
+    if isinstance(bed_IO, PairColumns):
+        return bed_IO
+    c1, p1, c2, p2, mark = read_pairs(bed_IO, order, chroms, layout)
+    return PairColumns(c1, p1, c2, p2, mark, device)
+
+
+def bin_traditional(pairs: PairColumns, genome: dict, wholeRes, localRes, device=None):
+    """Device-resident binning: returns ({res: (bins, DenseBatch[1])}, {res: DenseBatch[nchrom]})
+    with chromosomes in ``Sort_Chromosomes`` order.  matrixBuilding.py:553-603."""
+    dev = require_cuda(device)
+    order = Sort_Chromosomes(genome)
+    whole, local = {}, {}
+    for res in wholeRes:
+        bins, total = _bins_from_genome(genome, res, [(c, c) for c in order])
+        W = DenseBatch([total], dev)
+        start = _start_table(bins, order, dev)
+        kernels.bin_pairs_whole(pairs, res, start, start, W)
+        whole[res] = (bins, W)
+    for res in localRes:
+        L = DenseBatch([genome[c] // res + 1 for c in order], dev)   # matrixBuilding.py:564
+        kernels.bin_pairs_local(pairs, res, L)
+        local[res] = L
+    return whole, local
+
+
+def WholeMatrixToSparseDict(Bins, Matrix):
+    """matrixBuilding.py:457-506.  ``Matrix`` may be a NumPy array (uploaded) or a 1-matrix
+    ``DenseBatch`` already in HBM.  Intra blocks: upper triangle; inter blocks ``c1_c2`` (c1
+    before c2 in sorted order): all non-zeros, block-local coordinates."""
+    W = Matrix if isinstance(Matrix, DenseBatch) else DenseBatch.from_numpy([np.asarray(Matrix)])
+    ld, base = W.lds[0], W.buf.data_ptr()
+    chroms = Sort_Chromosomes(Bins.keys())
+    out = {}
+    for i, ca in enumerate(chroms):
+        a0, a1 = Bins[ca][0], Bins[ca][1] + 1
+        out[ca] = kernels.dense_nonzero_records(base + 4 * (a0 * ld + a0), ld, a1 - a0, a1 - a0, True,
+                                                False, W.device)
+        for cb in chroms[i + 1:]:
+            b0, b1 = Bins[cb][0], Bins[cb][1] + 1
+            out[ca + "_" + cb] = kernels.dense_nonzero_records(base + 4 * (a0 * ld + b0), ld, a1 - a0,
+                                                               b1 - b0, False, False, W.device)
+    return out
+
+
+def IntraMatrixToSparseDict(Dict):
+    """matrixBuilding.py:508-524.  Values may be int or float NumPy matrices, or
+    ``(DenseBatch, index)`` / float64 device tensors produced by this package."""
+    out = {}
+    for chro, M in Dict.items():
+        if isinstance(M, torch.Tensor):              # float64 (n, n) device tensor
+            n = M.shape[0]
+            out[chro] = kernels.dense_nonzero_records(M.data_ptr(), M.stride(0), n, n, True, True, M.device)
+        elif isinstance(M, tuple):                   # (DenseBatch, i)
+            b, i = M
+            out[chro] = kernels.dense_nonzero_records(b.buf.data_ptr() + 4 * b.offsets[i], b.lds[i],
+                                                      b.sizes[i], b.sizes[i], True, False, b.device)
+        else:
+            M = np.asarray(M)
+            if np.issubdtype(M.dtype, np.floating):
+                t = torch.from_numpy(np.ascontiguousarray(M, dtype=np.float64)).to(require_cuda())
+                out[chro] = kernels.dense_nonzero_records(t.data_ptr(), t.stride(0), M.shape[0], M.shape[1],
+                                                          True, True, t.device)
+            else:
+                b = DenseBatch.from_numpy([M])
+                out[chro] = kernels.dense_nonzero_records(b.buf.data_ptr(), b.lds[0], b.sizes[0], b.sizes[0],
+                                                          True, False, b.device)
+    return out
+
+
+def TraditionalMatrixBuilding(bed_IO, genomeSize, wholeRes, localRes, chroms):
+    """matrixBuilding.py:528-613.  ``bed_IO``: stream of 23-column valid-pair lines (or a
+    ``PairColumns`` already in HBM).  Returns (Whole_Lib, Local_Lib) of structured arrays."""
+    genome = Load_Genome(genomeSize, chroms)
+    order = Sort_Chromosomes(genome)
+    dev = require_cuda()
+    pairs = _to_pair_columns(bed_IO, order, chroms, "valid23", dev)
+    whole, local = bin_traditional(pairs, genome, wholeRes, localRes, dev)
+    Whole_Lib = {res: WholeMatrixToSparseDict(bins, W) for res, (bins, W) in whole.items()}
+    Local_Lib = {res: IntraMatrixToSparseDict({c: (L, i) for i, c in enumerate(order)})
+                 for res, L in local.items()}
+    return Whole_Lib, Local_Lib
+
+
+def TraditionalMatrixInAllelic(bed_IO, genomeSize, wholeRes, localRes, chroms):
+    """matrixBuilding.py:793-854 -- same accumulation on the 4/5-column allelic beds; returns
+    the RAW dense matrices: ({res: {'Bins', 'Matrix'}}, {res: {chrom: ndarray int64}})."""
+    genome = Load_Genome(genomeSize, chroms)
+    order = Sort_Chromosomes(genome)
+    dev = require_cuda()
+    pairs = _to_pair_columns(bed_IO, order, chroms, "allelic", dev)
+    whole, local = bin_traditional(pairs, genome, wholeRes, localRes, dev)
+    Whole_Lib = {res: {"Bins": bins, "Matrix": W.to_numpy(0)} for res, (bins, W) in whole.items()}
+    Local_Lib = {res: {c: L.to_numpy(i) for i, c in enumerate(order)} for res, L in local.items()}
+    return Whole_Lib, Local_Lib
+
+
+def bin_haplotype_local(pairs: PairColumns, genome: dict, res: int, onesided: bool, out: DenseBatch = None,
+                        device=None):
+    """Per-chromosome haplotype matrices from an M_M or P_P bed: 'Both' pairs symmetric
+    (matrixBuilding.py:1153-1161), or -- ``onesided`` -- the R1/R2 pairs added asymmetrically
+    on top of ``out`` (:1295-1301, :1409-1415)."""
+    dev = require_cuda(device)
+    order = Sort_Chromosomes(genome)
+    L = out if out is not None else DenseBatch([genome[c] // res + 1 for c in order], dev)
+    kernels.bin_pairs_local(pairs, res, L, _abi.HC_BIN_ONESIDED if onesided else _abi.HC_BIN_SYM_BOTH)
+    return L
+
+
+# ======================================================================================
+# (c) two-step allelic correction
+# ======================================================================================
+def _gap_array(idx_t, count):
+    # the reference returns np.array(python list): int64, or float64 when empty
+    return idx_t[:count].cpu().numpy().astype(np.int64) if count else np.array([])
+
+
+def two_step_device(T: DenseBatch, ti: int, M: DenseBatch, mi: int, P: DenseBatch, pi: int):
+    """TwoStepCorrection on matrices already in HBM; returns device float64 tensors and the
+    host gap arrays."""
+    n, dev = T.sizes[ti], T.device
+    assert M.sizes[mi] == n and P.sizes[pi] == n
+    tp, mp, pp = (b.buf.data_ptr() + 4 * b.offsets[i] for b, i in ((T, ti), (M, mi), (P, pi)))
+    rs_t, _ = kernels.rowstats(tp, T.lds[ti], n, n, dev, want_nnz=False)
+    rs_m, nz_m = kernels.rowstats(mp, M.lds[mi], n, n, dev)
+    rs_p, nz_p = kernels.rowstats(pp, P.lds[pi], n, n, dev)
+    alpha, (gf_m, gi_m), (gf_p, gi_p), ngap = kernels.twostep_alpha(
+        rs_t, rs_m, rs_p, nz_m, nz_p, n, n, _abi.HC_GAP_PERCENTILE, dev)
+    ng = ngap.cpu().numpy()
+    nor_m = kernels.twostep_correct(mp, M.lds[mi], n, alpha, gf_m, ng[0] > 0, rs_m, dev)
+    nor_p = kernels.twostep_correct(pp, P.lds[pi], n, alpha, gf_p, ng[1] > 0, rs_p, dev)
+    return nor_m, nor_p, _gap_array(gi_m, int(ng[0])), _gap_array(gi_p, int(ng[1]))
+
+
+def TwoStepCorrection(TM, MM, PM):
+    """matrixBuilding.py:984-1023 -> (Nor_MM, Nor_PM, Gap_M, Gap_P)."""
+    b = DenseBatch.from_numpy([np.asarray(TM), np.asarray(MM), np.asarray(PM)])
+    nor_m, nor_p, gap_m, gap_p = two_step_device(b, 0, b, 1, b, 2)
+    return nor_m.cpu().numpy(), nor_p.cpu().numpy(), gap_m, gap_p
+
+
+def IntraChromMatrixCorrection(Tra_Lib, Hap_Lib):
+    """matrixBuilding.py:1026-1041 -> (Nor_Lib, Gap_Lib) keyed 'M'+chrom / 'P'+chrom."""
+    Nor_Lib, Gap_Lib = {}, {}
+    for chro in Tra_Lib.keys():
+        a, b, ga, gb = TwoStepCorrection(Tra_Lib[chro], Hap_Lib["M" + chro], Hap_Lib["P" + chro])
+        Nor_Lib["M" + chro], Nor_Lib["P" + chro] = a, b
+        Gap_Lib["M" + chro], Gap_Lib["P" + chro] = ga, gb
+    return Nor_Lib, Gap_Lib
+
+
+def GenomeWideMatrixCorrection(Bins_Pos, Hap_Bins_Pos, T_M, H_M):
+    """matrixBuilding.py:857-901 -- low-resolution genome-wide haplotype matrix: per-chromosome
+    alpha from the intra blocks (gaps by the fixed 0.1 coverage rule on the traditional block),
+    concatenated in sorted chromosome order and repeated for the P half; H/alpha ->
+    sum-symmetrise -> Correct_VC(2/3) -> rescale to the raw mean."""
+    dev = require_cuda()
+    Tb = DenseBatch.from_numpy([np.asarray(T_M)])
+    Hb = DenseBatch.from_numpy([np.asarray(H_M)])
+    n_h = Hb.sizes[0]
+    alphas = {}
+    for chro, (lo, hi) in Bins_Pos.items():
+        n = hi - lo + 1
+        ml, pl = Hap_Bins_Pos["M" + chro][0], Hap_Bins_Pos["P" + chro][0]
+        tptr = Tb.buf.data_ptr() + 4 * (lo * Tb.lds[0] + lo)
+        mptr = Hb.buf.data_ptr() + 4 * (ml * Hb.lds[0] + ml)
+        pptr = Hb.buf.data_ptr() + 4 * (pl * Hb.lds[0] + pl)
+        rs_t, nz_t = kernels.rowstats(tptr, Tb.lds[0], n, n, dev)
+        rs_m, _ = kernels.rowstats(mptr, Hb.lds[0], n, n, dev, want_nnz=False)
+        rs_p, _ = kernels.rowstats(pptr, Hb.lds[0], n, n, dev, want_nnz=False)
+        alpha, _, _, _ = kernels.twostep_alpha(rs_t, rs_m, rs_p, nz_t, None, n, n, _abi.HC_GAP_FIXED, dev)
+        alphas[chro] = alpha
+    alpha = torch.cat([alphas[c] for c in Sort_Chromosomes(alphas.keys())])
+    alpha = torch.cat([alpha, alpha])                      # matrixBuilding.py:892
+    rs_h, _ = kernels.rowstats(Hb.buf.data_ptr(), Hb.lds[0], n_h, n_h, dev, want_nnz=False)
+    out = kernels.twostep_correct(Hb.buf.data_ptr(), Hb.lds[0], n_h, alpha, None, False, rs_h, dev)
+    return out.cpu().numpy()
+
+
+# ======================================================================================
+# (b) ICE  (`cooler balance`, call sites matrixBuilding.py:708, :713, :1537, :1542)
+# ======================================================================================
+def ice_balance_dense(mats, chrom_offsets=None, ignore_diags=1, mad_max=5, min_nnz=10, min_count=0,
+                      tol=1e-5, max_iters=200, rescale_marginals=True):
+    """Balance dense symmetric matrices.
+
+    ``mats``: list of square integer matrices / a ``DenseBatch`` -> ``--cis-only`` semantics
+    (each matrix is one chromosome with its own loop, scale and early exit; weights are
+    returned concatenated).  With ``chrom_offsets`` (nchrom+1 bin offsets) and ONE matrix ->
+    genome-wide balancing of that matrix (`cooler balance` without --cis-only)."""
+    batch = mats if isinstance(mats, DenseBatch) else DenseBatch.from_numpy([np.asarray(m) for m in mats])
+    off = None
+    if chrom_offsets is not None:
+        assert len(batch) == 1, "genome-wide balancing takes exactly one matrix"
+        off = torch.tensor(np.asarray(chrom_offsets, dtype=np.int64), device=batch.device)
+    return kernels.ice_balance_dense(batch, off, ignore_diags=ignore_diags, mad_max=mad_max,
+                                     min_nnz=min_nnz, min_count=min_count, tol=tol, max_iters=max_iters,
+                                     rescale_marginals=rescale_marginals)

@@ -1,0 +1,185 @@
+/*
+ * hichap_b200.h -- C ABI of libhichap_b200.so: the B200 (sm_100a) implementation of the
+ * hot path of HiCHap's `matrix` stage (reference: HiCHap/matrixBuilding.py).
+ *
+ * The reference is pure Python and has no FFI of its own; its boundary for this path is the
+ * set of Python callables in HiCHap/matrixBuilding.py plus the `cooler balance` command line.
+ * Each entry point below names the reference code (file:line, relative to the reference
+ * root) whose arithmetic it replaces.  The Python mirror of those callables lives in
+ * hichap_master_b200/matrixBuilding.py and binds this ABI with ctypes.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with `h_` (host).  The caller
+ *     owns all memory; the library borrows it for the duration of the (stream-ordered) call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Return value: 0 = success, negative = error; hc_last_error() returns the message of the
+ *     last failing call on the calling thread.
+ *   - Dense matrices are int32 row-major with leading dimension `ld` (elements, multiple of 4,
+ *     rows 16-byte aligned); a "dense batch" is one buffer holding several such matrices,
+ *     described by three small device tables (element offset, side n, ld per matrix).
+ *   - No CPU fallback exists: every entry point launches CUDA kernels.
+ */
+#ifndef HICHAP_B200_H
+#define HICHAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_OK 0
+#define HC_ERR_CUDA (-1)
+#define HC_ERR_ARG (-2)
+#define HC_ERR_NCCL (-3)
+#define HC_ERR_UNSUPPORTED (-4)
+
+#define HC_ABI_VERSION 1
+
+int hc_version(void);
+const char* hc_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+int64_t hc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) Valid-pair binning into dense integer tiles.
+ * Pairs are columnar int32 (chromosome index into the sorted chromosome table, fragment
+ * mid-point); a chromosome index < 0 means "filtered out" (matrixBuilding.py:577-580).
+ * `mark` (nullable) is 0=Both 1=R1 2=R2 3=other (matrixBuilding.py:1133, :1274, :1290).
+ * ---------------------------------------------------------------------------------------- */
+#define HC_BIN_SYM_ALL 0   /* every pair, symmetric:  M[b1][b2]++ and, if b1!=b2, M[b2][b1]++ */
+#define HC_BIN_SYM_BOTH 1  /* only mark==Both, symmetric (matrixBuilding.py:1131-1161)        */
+#define HC_BIN_ONESIDED 2  /* only mark!=Both: R1 -> M[b1][b2]++, else M[b2][b1]++ (:1295-1301) */
+
+/* Per-chromosome ("local") matrices: replaces the loop at matrixBuilding.py:595-603 (and
+ * :844-852, :1153-1161, :1191-1199, :1295-1301, :1409-1415).  Only pairs with c1==c2 count;
+ * bin = pos / res.  Pairs whose bin falls outside the matrix are counted into *oob (nullable)
+ * instead of being applied (the reference would raise IndexError). */
+int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                       const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                       int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                       const int32_t* mat_ld, int32_t nchrom, unsigned long long* oob,
+                       void* stream);
+
+/* Genome-wide ("whole") matrix: replaces matrixBuilding.py:582-592 (and :831-841, :1144-1151,
+ * :1182-1189, :1217-1221, :1239-1243, :1285-1293).  bin1 = p1/res + start1[c1],
+ * bin2 = p2/res + start2[c2]; start tables are device int64[nchrom].  HC_BIN_ONESIDED only
+ * applies cis pairs (c1==c2); the inter-chromosomal one-sided branch is the reference's
+ * neighbourhood imputation, which is outside this library. */
+int hc_bin_pairs_whole(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                       const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                       const int64_t* start1, const int64_t* start2, int32_t nchrom,
+                       int32_t* M, int32_t total, int64_t ld, unsigned long long* oob,
+                       void* stream);
+
+/* Dense -> sparse marshalling: replaces np.triu/np.nonzero at matrixBuilding.py:489-503 and
+ * :515-521.  Two calls: count (writes row_ptr[nrows+1], exclusive prefix sum, row-major order)
+ * then extract (bin1, bin2 block-local; val).  triu=1 keeps col>=row only.
+ * `is_f64` selects int32 (0) or float64 (1) element type for M / val. */
+int hc_dense_nonzero_count(const void* M, int64_t ld, int32_t nrows, int32_t ncols, int32_t triu,
+                           int32_t is_f64, int64_t* row_ptr, void* stream);
+int hc_dense_nonzero_extract(const void* M, int64_t ld, int32_t nrows, int32_t ncols, int32_t triu,
+                             int32_t is_f64, const int64_t* row_ptr, int32_t* bin1, int32_t* bin2,
+                             void* val, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) ICE balancing == `cooler balance --ignore-diags K [--cis-only]`
+ * (call sites matrixBuilding.py:708, :713, :1537, :1542, :1761, :1766; arithmetic restated in
+ * oracle/cooler_ice.py from cooler.balance.balance_cooler).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hc_ice_params {
+    double tol;            /* 1e-5 */
+    double mad_max;        /* 5    */
+    int32_t min_nnz;       /* 10   */
+    int32_t min_count;     /* 0    */
+    int32_t ignore_diags;  /* HiCHap passes 1 */
+    int32_t max_iters;     /* 200  */
+    int32_t rescale_marginals; /* 1 */
+    int32_t poll_every;    /* host polls the device-side done counter every this many launches */
+} hc_ice_params;
+
+/* Filter marginals of a dense batch of symmetric matrices (one balancing problem per matrix,
+ * bins concatenated: problem p owns bias[bin_off[p] .. bin_off[p+1])).  Writes, per bin, the
+ * number of non-zero off-band pixels (nnz_marg) and their sum (marg, as float64).
+ * Replaces the two pre-iteration marginalisations of balance_cooler. */
+int hc_ice_dense_marginals(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                           const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                           int32_t ignore_diags, double* nnz_marg, double* marg, void* stream);
+
+/* Bin filters -> initial bias (1 = keep, 0 = masked): min_nnz, min_count, then MAD-max on
+ * log-marginals normalised by the per-chromosome median (chrom_off: device int64[nchrom+1]
+ * over the concatenated bins).  `marg` is modified in place (divided by the chromosome
+ * medians) exactly as cooler does.  `work` must hold 2*nbins doubles. */
+int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t nbins,
+                       const int64_t* chrom_off, int32_t nchrom, const hc_ice_params* h_params,
+                       double* bias, double* work, void* stream);
+
+/* Per-problem results of a balancing run (device array of nprob of these). */
+typedef struct hc_ice_result {
+    double scale;      /* mean of the non-zero marginals at the last iteration (NaN if empty) */
+    double var;        /* their population variance                                           */
+    int32_t iters;     /* iterations executed                                                 */
+    int32_t converged; /* var < tol                                                           */
+} hc_ice_result;
+
+/* Host-side record of one balancing run. */
+typedef struct hc_ice_run_info {
+    int32_t launches; /* kernels launched by the call (iterations + finalise)                  */
+    float loop_ms;    /* device time of the iteration loop (CUDA events on `stream`)           */
+} hc_ice_run_info;
+
+/* Iterate every problem of the dense batch to convergence, independently (own loop, scale and
+ * early exit -- cooler's _balance_cisonly; one problem == _balance_genomewide).
+ * bias: in = initial bias from the filters, out = final weights (NaN for masked bins, divided
+ * by sqrt(scale) when rescale_marginals).  work: 3*nbins doubles.  The reduction over the
+ * marginals, the bias update, the rescale and the convergence test all run on the device
+ * inside the same kernel that streams the matrix; the host only polls a done counter. */
+int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                         const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                         const int32_t* h_mat_n, const hc_ice_params* h_params, double* bias,
+                         double* work, hc_ice_result* results, hc_ice_run_info* h_info, void* stream);
+
+/* Upper-triangular CSR variant (genome-wide matrices too large for dense tiles): one problem,
+ * rows [row_lo,row_hi) held by this rank (row-block sharding), full-length bias.  See csr.h
+ * section below. */
+
+/* ------------------------------------------------------------------------------------------
+ * (c) Two-step allelic correction (matrixBuilding.py:984-1023 TwoStepCorrection, with
+ * Gap_defined :915-929, Trans2symmetry :945-979, Correct_VC :780-790).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Row sums (int64) and non-zero counts (int32) of an int32 matrix view.  Replaces the row
+ * loops at matrixBuilding.py:904-912 and :994-995. */
+int hc_rowstats_i32(const int32_t* M, int64_t ld, int32_t nrows, int32_t ncols, int64_t* rowsum,
+                    int32_t* rownnz, void* stream);
+
+#define HC_GAP_PERCENTILE 0 /* Gap_defined: min(percentile(cov[cov!=0], 25), 0.2)  (:915-929) */
+#define HC_GAP_FIXED 1      /* Gap_definedLowRes: 0.1                               (:742-753) */
+
+/* O(n) part of the correction, on device: coverage -> gap rows of MM and PM, SNP-density
+ * factor alpha = (rowsum MM + rowsum PM) / (rowsum TM + 1), normalised by its max over the
+ * non-gap rows, zeros -> 1, floored at its 20th percentile (matrixBuilding.py:989-1005).
+ * gap_union=1: non-gap = NonGap(MM) | NonGap(PM) (TwoStepCorrection); gap_union=0 with
+ * nnz_b == NULL: gaps from matrix A only (GenomeWideMatrixCorrection :872-885, where A is the
+ * traditional block).  Outputs: alpha[n]; gap flags (uint8[n]) and ascending index lists with
+ * counts ngap[2].  work: 2*n doubles. */
+int hc_twostep_alpha(const int64_t* rowsum_t, const int64_t* rowsum_m, const int64_t* rowsum_p,
+                     const int32_t* nnz_a, const int32_t* nnz_b, int32_t n, int32_t ncols,
+                     int32_t gap_mode, double* alpha, uint8_t* gapflag_a, uint8_t* gapflag_b,
+                     int32_t* gapidx_a, int32_t* gapidx_b, int32_t* ngap, double* work,
+                     void* stream);
+
+/* Fused  X / alpha[:,None] -> Trans2symmetry -> Correct_VC(2/3) -> rescale to the raw mean
+ * for ONE int32 matrix X (n x n, leading dimension ld).  gapflag == NULL or *h_ngap == 0
+ * selects the reference's "no gap rows" rule (S_ij + S_ji, matrixBuilding.py:948-952 and
+ * Trans2symmetryLowRes :770-776); otherwise both-gap -> max, else mean.  out is float64
+ * n x n with leading dimension ld_out.  work: hc_twostep_work_bytes(n) bytes. */
+int64_t hc_twostep_work_bytes(int32_t n);
+int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const double* alpha,
+                       const uint8_t* gapflag, int32_t has_gap, const int64_t* rowsum_x,
+                       double* out, int64_t ld_out, void* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICHAP_B200_H */

@@ -1,0 +1,74 @@
+"""CPU tests of the host-side mirror: genome/bin tables and the text -> columnar parser,
+against the oracle restatement (itself pinned to the reference)."""
+import io
+
+import numpy as np
+import pytest
+
+from conftest import CHROMS, SMALL_GENOME, load_golden
+from hichap_master_b200 import pairs, synth
+from oracle import hichap_oracle as ho
+
+
+def test_genome_tables_match_oracle(small_genome_file):
+    from hichap_master_b200 import matrixBuilding as mb
+    for chroms in (["#", "X"], [], ["#"], ["X", "Y"]):
+        genome = mb.Load_Genome(small_genome_file, chroms)
+        assert genome == ho.load_genome(small_genome_file, chroms)
+        assert mb.Sort_Chromosomes(genome) == ho.sort_chromosomes(genome)
+        for res in (40000, 500000, 4_800_000):
+            assert mb.Get_Chro_Bins(small_genome_file, res, chroms) == ho.chro_bins(genome, res)
+            assert mb.Get_Chro_Bins_Haplotypes(small_genome_file, res, chroms) == ho.chro_bins_haplotypes(genome, res)
+        hg = mb.Load_HaplotypeGenome(small_genome_file, chroms)
+        assert set(hg) == {t + c for c in genome for t in "MP"}
+
+
+def test_lstrip_chr_is_a_character_set():
+    from hichap_master_b200 import matrixBuilding as mb
+    # 'chrchr1' -> '1', 'rch2' -> '2' (str.lstrip strips the set {c,h,r}; matrixBuilding.py:359)
+    assert mb.Sort_Chromosomes(["chrchr1", "rch2", "chrX"]) == ["1", "2", "X"]
+
+
+@pytest.mark.parametrize("as_bytes", [False, True])
+def test_valid23_parser_matches_oracle(small_genome_file, as_bytes):
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    order = ho.sort_chromosomes(genome)
+    names = [c for c in SMALL_GENOME if c != "M"]
+    big = {c: SMALL_GENOME[c] for c in names}
+    c1, p1, c2, p2 = synth.genome_pairs(big, names, 2000, 5, trans_frac=0.3)
+    text = "".join(synth.valid23_lines(names, c1, p1, c2, p2))
+    exp = ho.parse_pairs(text.splitlines(True), genome, CHROMS, "valid23")
+    stream = io.BytesIO(text.encode()) if as_bytes else io.StringIO(text)
+    got = pairs.read_pairs(stream, order, CHROMS, "valid23")
+    keep = (got[0] >= 0) & (got[2] >= 0)          # the product keeps dropped rows as chrom -1
+    for a, b in zip(got[:4], exp[:4]):
+        assert np.array_equal(a[keep], b)
+    assert got[4] is None
+
+
+def test_allelic_parser_ragged_columns(small_genome_file):
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    order = ho.sort_chromosomes(genome)
+    text = ("chr1\t100\tchr1\t90000\tBoth\n"
+            "chr2\t5\tchrX\t7\n"                      # 4-column Bi_Allelic style line
+            "chr10\t1\tchr10\t2\tR1\n"
+            "chrY\t1\tchr1\t2\tR2\n"                  # dropped by the filter
+            "chrX\t11\tchrX\t12\tR2\n")
+    exp = ho.parse_pairs(text.splitlines(True), genome, CHROMS, "allelic")
+    got = pairs.read_pairs(io.StringIO(text), order, CHROMS, "allelic")
+    keep = (got[0] >= 0) & (got[2] >= 0)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a[keep], b)
+    assert list(got[4]) == [0, 3, 1, 2, 2]
+    # iterable of lines (what `for line in bed_IO` accepts) and empty input
+    got2 = pairs.read_pairs(text.splitlines(True), order, CHROMS, "allelic")
+    assert all(np.array_equal(a, b) for a, b in zip(got, got2))
+    empty = pairs.read_pairs(io.StringIO(""), order, CHROMS, "allelic")
+    assert empty[0].size == 0 and empty[4].size == 0
+
+
+def test_unknown_chromosome_raises_keyerror(small_genome_file):
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    order = ho.sort_chromosomes(genome)
+    with pytest.raises(KeyError):
+        pairs.read_pairs(io.StringIO("chr7\t1\tchr1\t2\tBoth\n"), order, CHROMS, "allelic")
