@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- the matrix-stage hot path on BASELINE.json's config C2:
+hg19 chr1-22,X intra-chromosomal matrices at 40 kb from synthetic cis valid pairs, binned on
+the GPU and ICE-balanced (`cooler balance --ignore-diags 1 --cis-only` semantics) to convergence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+
+One "step" = zero the dense tiles, bin all pairs, run the bin filters and iterate every
+chromosome to convergence.  `value` = device-resident step time (ms, lower is better);
+`e2e` = the same through the host-facing call: pinned host columns -> HBM, the step, the
+upper-triangular records and the weight vector back to the host.  N > 1: chromosomes are
+LPT-sharded over ranks (no collective on the data path); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 40000
+METRIC = "matrix_stage_time_to_ice_convergence"
+UNIT = "ms"
+
+
+def c2_genome():
+    from hichap_master_b200 import synth
+    g = {c: l for c, l in synth.HG19.items() if c not in ("Y", "M")}
+    order = [str(i) for i in range(1, 23)] + ["X"]
+    return g, order
+
+
+def pair_shares(genome, order, total):
+    lens = np.array([genome[c] for c in order], dtype=np.float64)
+    share = np.floor(total * lens / lens.sum()).astype(np.int64)
+    share[0] += total - share.sum()
+    return share
+
+
+def workload_name(pairs):
+    return ("C2: hg19 chr1-22,X intra-chromosomal 40 kb matrices, %d synthetic cis valid pairs, "
+            "binning + cis-only ICE (ignore_diags=1, cooler defaults) to convergence" % pairs)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hichap_master_b200 import _abi, kernels, shard, synth
+    from hichap_master_b200.device import PairColumns
+    from hichap_master_b200.pipeline import HostPairs, LocalStage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    genome, order = c2_genome()
+    sizes_all = [genome[c] // RES + 1 for c in order]
+    shares = pair_shares(genome, order, args.pairs)
+    mine = shard.chromosome_shards(sizes_all, world)[rank]
+    sizes = [sizes_all[i] for i in mine]
+
+    # ---- synthetic inputs, generated on the device, one seeded stream per chromosome ---------
+    cs, p1s, p2s = [], [], []
+    for li, gi in enumerate(mine):
+        c = order[gi]
+        _, a, _, b = synth.genome_pairs_torch({c: genome[c]}, [c], int(shares[gi]), 2000 + gi, dev)
+        cs.append(torch.full((a.numel(),), li, dtype=torch.int32, device=dev)); p1s.append(a); p2s.append(b)
+    c1 = torch.cat(cs); p1 = torch.cat(p1s); p2 = torch.cat(p2s)
+    del cs, p1s, p2s
+    g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+    perm = torch.randperm(c1.numel(), generator=g, device=dev)
+    c1, p1, p2 = c1[perm].contiguous(), p1[perm].contiguous(), p2[perm].contiguous()
+    del perm
+    n_local = int(c1.numel())
+    pairs = PairColumns(c1, p1, c1, p2, device=dev)
+    stage = LocalStage(sizes, n_local, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """device time of `steps` calls, max over ranks (ms per step) + last result"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), out
+
+    step = lambda: stage.run(pairs, RES, records=False, weights_to_host=False)
+    for _ in range(args.warmup):
+        step()
+    launches0 = _abi.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, out = timed(step, args.steps)
+    launches = (_abi.launch_count() - launches0) // args.steps
+    # roofline of the dominant kernel (the fused ICE iteration), from the same timed steps
+    iters = out["results"]["iters"].astype(np.int64)
+    ice_bytes = float(sum(int(it) * 4 * n * n for it, n in zip(iters, sizes)))
+    loop_ms = float(out["info"].loop_ms)
+    n_iter_launches = int(out["info"].launches) - 1
+
+    # ---- end to end through the host-facing call ---------------------------------------------
+    host = HostPairs(c1.cpu(), p1.cpu(), c1.cpu(), p2.cpu())
+    e2e_step = lambda: stage.run(stage.upload(host), RES, records=True, weights_to_host=True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        o2 = e2e_step()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e, o2 = timed(e2e_step, e2e_steps)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = torch.tensor([float(host.nbytes)], dtype=torch.float64, device=dev)
+    d2h = torch.tensor([float(o2["d2h_bytes"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d); dist.all_reduce(d2h)
+
+    # ---- per-kernel breakdown (rank 0, outside the timed regions) ----------------------------
+    breakdown = None
+    if rank == 0:
+        def ev_time(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        t_zero = ev_time(lambda: stage.batch.buf.zero_())
+        t_bin = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local(pairs, RES, stage.batch, check_bounds=False))) - t_zero
+        params = kernels.ice_params()
+        t_filt = ev_time(lambda: kernels.ice_dense_filters(stage.batch, params))
+        sq = float(sum(n * n for n in sizes))
+        breakdown = {
+            "zero_tiles_ms": t_zero, "binning_ms": t_bin, "ice_filters_ms": t_filt, "ice_loop_ms": loop_ms,
+            "binning_GBps": 16.0 * n_local / (t_bin * 1e6), "binning_Gpairs_per_s": n_local / (t_bin * 1e6),
+            "ice_filters_GBps": 4.0 * sq / (t_filt * 1e6),
+            "ice_iters": [int(i) for i in iters], "ice_iter_launches": n_iter_launches,
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ice_bytes / (loop_ms * 1e6) if loop_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32 counts / f64 weights", "data": "synthetic",
+        "config": {"workload": workload_name(args.pairs), "pairs": args.pairs, "bins": int(sum(sizes_all)),
+                   "resolution": RES, "chromosomes": len(order),
+                   "parallelism": "chromosomes LPT-sharded by N^2 over %d GPU(s), no collective" % world,
+                   "l2": "inputs larger than L2 (%.1f GB pair columns, %.2f GB int32 tiles on rank 0)"
+                         % (16e-9 * n_local, 4e-9 * stage.batch.numel)},
+        "throughput_Mpairs_per_s": args.pairs / (ms_step * 1e3),
+        "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
+                "d2h_bytes_per_step": int(d2h.item()), "steps": e2e_steps,
+                "Mpairs_per_s": args.pairs / (ms_e2e * 1e3)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "ice_dense_iter_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
+                     "algorithmic_bytes_per_launch": ice_bytes / max(n_iter_launches, 1),
+                     "launches": n_iter_launches, "avg_launch_ms": loop_ms / max(n_iter_launches, 1),
+                     "traffic": None},
+        "breakdown": breakdown, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.pairs, threads=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------
+SAMPLE_CHROMS = ["21", "22"]
+
+
+def _cpu_one_chrom(job):
+    """oracle port on one chromosome: bin (NumPy restatement) + cis-only ICE restatement"""
+    from oracle import cooler_ice, hichap_oracle as ho
+    c, length, p1, p2 = job
+    n = length // RES + 1
+    z = np.zeros(p1.size, np.int32)
+    t0 = time.perf_counter()
+    M = ho.bin_local_dense(z, p1, z, p2, [n], RES)[0]
+    rec = ho.dense_to_triu_records(M)
+    t1 = time.perf_counter()
+    w, st = cooler_ice.balance(rec["bin1"], rec["bin2"], rec["IF"].astype(np.int32), n, [0, n], cis_only=True)
+    t2 = time.perf_counter()
+    return c, t1 - t0, t2 - t1, int(st["iters"][0]), int(rec.size)
+
+
+def _cpu_sample(pairs_total):
+    from hichap_master_b200 import synth
+    genome, order = c2_genome()
+    shares = pair_shares(genome, order, pairs_total)
+    jobs = []
+    for c in SAMPLE_CHROMS:
+        i = order.index(c)
+        a, b = synth.cis_pairs(c, genome[c], int(shares[i]), 2000 + i)
+        jobs.append((c, genome[c], a, b))
+    n_sample = sum(j[2].size for j in jobs)
+    return jobs, n_sample
+
+
+def cpu_baseline(pairs_total, threads=1, sample=None):
+    jobs, n_sample = sample if sample is not None else _cpu_sample(pairs_total)
+    t0 = time.perf_counter()
+    if threads > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(threads, len(jobs))) as pool:
+            res = pool.map(_cpu_one_chrom, jobs)
+        used = min(threads, len(jobs))
+    else:
+        res = [_cpu_one_chrom(j) for j in jobs]
+        used = 1
+    wall = time.perf_counter() - t0
+    scale = pairs_total / float(n_sample)
+    return {"value": wall * 1e3 * scale, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": ("oracle port (NumPy restatement of matrixBuilding.py:595-603 + cooler balance --cis-only) on "
+                       "chromosomes %s of the same workload = %d of %d pairs, %.1f s measured; value is that time "
+                       "x %.1f (pair ratio) -- extrapolated. The reference's own interpreted binning loop is "
+                       "2.64 us/pair/resolution (SURVEY.md probe), slower than this vectorised port"
+                       % ("+".join(SAMPLE_CHROMS), n_sample, pairs_total, wall, scale)),
+            "measured_s": wall, "scale": scale,
+            "per_chrom": [{"chrom": c, "bin_s": tb, "ice_s": ti, "iters": it, "nnz": nz} for c, tb, ti, it, nz in res],
+            "host_cores": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python-2 reference cannot be
+    installed) on the host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    cb = None
+    sample = _cpu_sample(args.pairs)
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(args.pairs, threads=threads, sample=sample)
+        if i >= args.warmup:
+            times.append(cb["value"])
+    v = float(np.mean(times))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int64 counts / f64 weights", "data": "synthetic",
+            "config": {"workload": workload_name(args.pairs), "pairs": args.pairs, "resolution": RES},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=400_000_000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 3)
+        args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
