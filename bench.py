@@ -175,6 +175,15 @@ def run_ours(args):
     n_iter_launches = int(out["info"].launches) - 1
 
     # ---- end to end through the host-facing call ---------------------------------------------
+    if args.skip_e2e:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"tuning_only": True, "ms_per_step": ms_step, "ice_loop_ms": loop_ms,
+                              "ice_GBps": ice_bytes / (loop_ms * 1e6), "ice_launches": n_iter_launches,
+                              "variant": os.environ.get("HC_ICE_VARIANT"), "waves": os.environ.get("HC_ICE_WAVES")}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     host = HostPairs(c1.cpu(), p1.cpu(), c1.cpu(), p2.cpu())
     e2e_step = lambda: stage.run(stage.upload(host), RES, records=True, weights_to_host=True)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -341,6 +350,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=400_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="kernel tuning runs only: no e2e leg (line is not a bench result)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 3)

@@ -47,6 +47,8 @@ SIGNATURES = {
     "hc_bin_pairs_whole": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _I64, _P, _P]),
     "hc_dense_nonzero_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_dense_nonzero_extract": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "hc_dense_batch_triu_count": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _P]),
+    "hc_dense_batch_triu_records": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _P, _P]),
     "hc_ice_dense_marginals": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "hc_ice_filter_bins": (C.c_int, [_P, _P, _I64, _P, _I32, C.POINTER(IceParams), _P, _P, _P]),
     "hc_ice_dense_balance": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.POINTER(_I32), C.POINTER(IceParams),
@@ -55,6 +57,23 @@ SIGNATURES = {
     "hc_twostep_alpha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_twostep_work_bytes": (C.c_int64, [_I32]),
     "hc_twostep_correct": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P]),
+    "hc_pairs_to_keys": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "hc_sort_work_bytes": (C.c_int64, [_I64]),
+    "hc_sort_keys_u64": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, C.POINTER(_I32), _P]),
+    "hc_csr_work_bytes": (C.c_int64, [_I64]),
+    "hc_csr_count": (C.c_int, [_P, _I64, _P, _P, C.POINTER(_I64), _P]),
+    "hc_csr_emit": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P]),
+    "hc_csr_upper_count": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "hc_csr_upper_emit": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "hc_ice_csr_marginals": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P]),
+    "hc_ice_csr_work_bytes": (C.c_int64, [_I64, _I32]),
+    "hc_ice_csr_balance": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, C.POINTER(_I64), C.POINTER(IceParams),
+                                     _P, _P, _P, C.POINTER(IceRunInfo), _P, _P]),
+    "hc_nccl_available": (C.c_int, []),
+    "hc_nccl_unique_id": (C.c_int, [_P]),
+    "hc_nccl_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "hc_nccl_comm_destroy": (C.c_int, [_P]),
+    "hc_nccl_allreduce_sum_f64": (C.c_int, [_P, _P, _I64, _P]),
 }
 
 _lib = None

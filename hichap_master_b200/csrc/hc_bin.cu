@@ -151,7 +151,88 @@ row_nonzero_extract_kernel(const T* __restrict__ M, int64_t ld, int nrows, int n
     }
 }
 
+// ---- whole batch at once: upper-triangular records in the reference's 24-byte layout ------
+struct Rec24 { long long bin1; long long bin2; double IF; };   // matrixBuilding.py:460-461 S_dtype
+
+__device__ __forceinline__ int batch_problem(const int64_t* __restrict__ bin_off, int nprob, int64_t g) {
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (bin_off[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+batch_triu_count_kernel(const int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off,
+                        const int32_t* __restrict__ mat_n, const int32_t* __restrict__ mat_ld,
+                        const int64_t* __restrict__ bin_off, int nprob, int64_t* __restrict__ row_cnt) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per (global) row
+    const int lane = threadIdx.x & 31;
+    if (g >= bin_off[nprob]) return;
+    const int p = batch_problem(bin_off, nprob, g);
+    const int r = (int)(g - bin_off[p]), n = mat_n[p];
+    const int32_t* row = mats + mat_off[p] + (int64_t)r * mat_ld[p];
+    int cnt = 0;
+    for (int j = r + lane; j < n; j += 32) cnt += (row[j] != 0);
+    cnt = warp_sum_i(cnt);
+    if (lane == 0) row_cnt[g] = cnt;
+}
+
+__global__ void __launch_bounds__(256)
+batch_triu_records_kernel(const int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off,
+                          const int32_t* __restrict__ mat_n, const int32_t* __restrict__ mat_ld,
+                          const int64_t* __restrict__ bin_off, int nprob, const int64_t* __restrict__ row_ptr,
+                          Rec24* __restrict__ rec) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= bin_off[nprob]) return;
+    const int p = batch_problem(bin_off, nprob, g);
+    const int r = (int)(g - bin_off[p]), n = mat_n[p];
+    const int32_t* row = mats + mat_off[p] + (int64_t)r * mat_ld[p];
+    int64_t out = row_ptr[g];
+    for (int base = r; base < n; base += 32) {
+        const int j = base + lane;
+        const int x = j < n ? row[j] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, x != 0);
+        if (x != 0) {
+            Rec24 v; v.bin1 = r; v.bin2 = j; v.IF = (double)x;
+            rec[out + __popc(m & ((1u << lane) - 1u))] = v;
+        }
+        out += __popc(m);
+    }
+}
+
+// multi-CTA exclusive scan is not needed: bins are O(1e5); one CTA with a 64-bit carry
 }  // namespace
+
+extern "C" int hc_dense_batch_triu_count(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                         const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                                         int64_t nbins, int64_t* row_ptr, void* stream) {
+    HC_REQUIRE(nprob > 0 && nbins >= 0, "nprob>0, nbins>=0");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nbins > 0) {
+        const int64_t blocks = (nbins * 32 + 255) / 256;
+        batch_triu_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(mats, mat_off, mat_n, mat_ld, bin_off, nprob, row_ptr);
+        HC_LAUNCH_CHECK();
+    }
+    HC_REQUIRE(nbins < (1ll << 31), "too many bins for the single-CTA scan");
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(row_ptr, (int)nbins);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int hc_dense_batch_triu_records(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                           const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                                           int64_t nbins, const int64_t* row_ptr, void* records, void* stream) {
+    HC_REQUIRE(nprob > 0 && nbins >= 0, "nprob>0, nbins>=0");
+    if (nbins == 0) return HC_OK;
+    const int64_t blocks = (nbins * 32 + 255) / 256;
+    batch_triu_records_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        mats, mat_off, mat_n, mat_ld, bin_off, nprob, row_ptr, reinterpret_cast<Rec24*>(records));
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
 
 extern "C" int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
                                   const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode, int32_t* mats,

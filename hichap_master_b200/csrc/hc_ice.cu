@@ -14,6 +14,7 @@
 #include <vector>
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include "hc_common.cuh"
 #include "hc_select.cuh"
 
@@ -123,142 +124,179 @@ ice_filter_mad_kernel(const double* __restrict__ marg, int64_t nbins, double mad
 // ---------------------------------------------------------------------------------------
 struct IceDenseArgs {
     const int32_t* mats; const int64_t* mat_off; const int32_t* mat_n; const int32_t* mat_ld;
-    const int64_t* bin_off;
+    const int64_t* pad_off;     // start of each problem in the padded (ld-strided, 128 B aligned) vectors
     const int32_t* cta_prob; const int32_t* cta_row0; const int32_t* cta_row1;
-    double* bias[2];   // ping-pong: launch k reads b_{k-2} from bias[k&1], writes b_{k-1} to bias[(k+1)&1]
-    double* marg[2];   // launch k reads marg_{k-1} from marg[(k-1)&1], writes marg_k to marg[k&1]
+    const int32_t* prob_ncta;   // CTAs working on each problem
+    int32_t* ticket;            // per problem: CTAs finished in this launch (reset by the last one)
+    double* bias;               // padded layout; updated in place by the tail of each problem
+    double* marg;               // padded layout; fresh marginals of this launch
     hc_ice_result* results; int32_t* done; int32_t* n_done;
     double tol; int kd; int max_iters;
 };
 
-__global__ void __launch_bounds__(1024)
+// one column chunk (128 columns, 4 per lane) of RG rows: acc[q] += sum_j w * A[rq][j] * b[j]
+template <int RG>
+__device__ __forceinline__ void consume_chunk(const int4 (&a)[RG], const double* __restrict__ b, int j, int jc,
+                                              int rg, int kd, int kspan, double (&acc)[RG]) {
+    const double2 b01 = *reinterpret_cast<const double2*>(b + j);        // through L1: reused by every row
+    const double2 b23 = *reinterpret_cast<const double2*>(b + j + 2);
+    const bool band = jc <= rg + RG - 1 + kspan && jc + 127 >= rg - kspan;   // warp-uniform
+#pragma unroll
+    for (int q = 0; q < RG; ++q) {
+        double x0 = (double)a[q].x, x1 = (double)a[q].y, x2 = (double)a[q].z, x3 = (double)a[q].w;
+        if (band) {
+            const int r = rg + q;
+            x0 *= band_weight(j, r, kd); x1 *= band_weight(j + 1, r, kd);
+            x2 *= band_weight(j + 2, r, kd); x3 *= band_weight(j + 3, r, kd);
+        }
+        acc[q] = fma(x0, b01.x, acc[q]); acc[q] = fma(x1, b01.y, acc[q]);
+        acc[q] = fma(x2, b23.x, acc[q]); acc[q] = fma(x3, b23.y, acc[q]);
+    }
+}
+
+template <int RG, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 ice_dense_iter_kernel(IceDenseArgs A, int k) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sb = reinterpret_cast<double*>(smem_raw);  // staged bias, ld doubles (padding = 0)
     __shared__ double red[32];
     __shared__ long long redll[32];
+    __shared__ int flag_s;
 
     const int p = A.cta_prob[blockIdx.x];
-    // the leader CTA of this same launch may set done[p] while we start: read it once, CTA-uniformly
-    __shared__ int done_s;
-    if (threadIdx.x == 0) done_s = *reinterpret_cast<volatile int32_t*>(A.done + p);
-    __syncthreads();
-    if (done_s) return;
+    if (A.done[p]) return;                 // set by the tail of an EARLIER launch: uniform for the CTA
     const int n = A.mat_n[p];
-    const int64_t ld = A.mat_ld[p], lo = A.bin_off[p];
+    const int ld = A.mat_ld[p];            // multiple of 128: every 128-column chunk is full
+    const int64_t lo = A.pad_off[p];
     const int row0 = A.cta_row0[blockIdx.x], row1 = A.cta_row1[blockIdx.x];
-    const bool leader = row0 == 0;
 
-    // ---- prologue: reduction over previous marginals, bias update, convergence test --------
-    if (k == 1) {
-        const double* b0 = A.bias[0] + lo;
-        for (int j = threadIdx.x; j < (int)ld; j += blockDim.x) sb[j] = j < n ? b0[j] : 0.0;
-    } else {
-        const double* mprev = A.marg[(k - 1) & 1] + lo;
-        const double* bprev = A.bias[k & 1] + lo;
-        double s = 0.0;
-        long long c = 0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const double m = mprev[j];
-            if (m != 0.0) { s += m; ++c; }
+    // ---- body: marg[r] = b[r] * sum_j w(r,j) A[r][j] b[j] -------------------------------------
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nchunk = ld >> 7;
+    const int32_t* mat = A.mats + A.mat_off[p];
+    const double* __restrict__ b = A.bias + lo;
+    double* mout = A.marg + lo;
+    const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
+    for (int rg = row0 + wid * RG; rg < row1; rg += nw * RG) {
+        const int nr = min(RG, row1 - rg);
+        const int32_t* base = mat + (int64_t)rg * ld + 4 * lane;
+        int roff[RG];                      // ragged last group: re-read the last valid row, discard below
+#pragma unroll
+        for (int q = 0; q < RG; ++q) roff[q] = min(q, nr - 1) * ld;
+        double acc[RG];
+#pragma unroll
+        for (int q = 0; q < RG; ++q) acc[q] = 0.0;
+        int c0 = 0;
+        for (; c0 + U <= nchunk; c0 += U) {   // RG x U independent 128-bit streaming loads in flight per lane
+            int4 a[U][RG];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < RG; ++q) a[u][q] = ld_stream_v4(base + roff[q] + (c0 + u) * 128);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                consume_chunk<RG>(a[u], b, (c0 + u) * 128 + 4 * lane, (c0 + u) * 128, rg, kd, kspan, acc);
         }
-        s = block_sum(s, red);
-        c = block_sum_ll(c, redll);
-        if (c == 0) {  // nothing left to balance: cooler sets bias = NaN, scale = NaN, var = 0
-            if (leader && threadIdx.x == 0) {
-                hc_ice_result r; r.scale = __longlong_as_double(0x7ff8000000000000ll); r.var = 0.0;
-                r.iters = k - 1; r.converged = 1;
-                A.results[p] = r; A.done[p] = 1; atomicAdd(A.n_done, 1);
-            }
-            return;
+        for (; c0 < nchunk; ++c0) {
+            int4 a[RG];
+#pragma unroll
+            for (int q = 0; q < RG; ++q) a[q] = ld_stream_v4(base + roff[q] + c0 * 128);
+            consume_chunk<RG>(a, b, c0 * 128 + 4 * lane, c0 * 128, rg, kd, kspan, acc);
         }
-        const double mean = s / (double)c;
-        double v = 0.0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const double m = mprev[j];
-            if (m != 0.0) { const double d = m - mean; v += d * d; }
+#pragma unroll
+        for (int q = 0; q < RG; ++q) {
+            const double sacc = warp_sum(acc[q]);
+            if (lane == 0 && q < nr) mout[rg + q] = b[rg + q] * sacc;
         }
-        const double var = block_sum(v, red) / (double)c;
-        double* bout = A.bias[(k + 1) & 1] + lo;
-        for (int j = threadIdx.x; j < (int)ld; j += blockDim.x) {
-            double b = 0.0;
-            if (j < n) {
-                double m = mprev[j] / mean;
-                if (m == 0.0) m = 1.0;
-                b = bprev[j] / m;
-                if (leader) bout[j] = b;
-            }
-            sb[j] = b;
-        }
-        if (var < A.tol || k - 1 >= A.max_iters) {
-            if (leader && threadIdx.x == 0) {
-                hc_ice_result r; r.scale = mean; r.var = var; r.iters = k - 1; r.converged = var < A.tol;
-                A.results[p] = r; A.done[p] = 1; atomicAdd(A.n_done, 1);
-            }
-            return;
-        }
+    }
+
+    // ---- tail: the last CTA of this problem reduces, updates the bias and tests convergence --
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // publish this CTA's marginals
+        const int t = atomicAdd(A.ticket + p, 1);
+        flag_s = (t == A.prob_ncta[p] - 1);
     }
     __syncthreads();
-
-    // ---- body: marg_k[r] = b[r] * sum_j w(r,j) A[r][j] b[j] ---------------------------------
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nvec = (int)(ld >> 2);
-    const int nchunk = (nvec + 31) >> 5;
-    const int32_t* mat = A.mats + A.mat_off[p];
-    double* mout = A.marg[k & 1] + lo;
-    const double2* sb2 = reinterpret_cast<const double2*>(sb);
-    const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
-    constexpr int U = 4;
-    for (int r = row0 + wid; r < row1; r += nw) {
-        const int32_t* row = mat + (int64_t)r * ld;
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int c0 = 0; c0 < nchunk; c0 += U) {
-            int4 a[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int v = (c0 + u) * 32 + lane;
-                a[u] = v < nvec ? ld_stream_v4(row + 4 * v) : make_int4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int v = (c0 + u) * 32 + lane;
-                if (v < nvec) {
-                    const double2 b01 = sb2[2 * v], b23 = sb2[2 * v + 1];
-                    double x0 = (double)a[u].x, x1 = (double)a[u].y, x2 = (double)a[u].z, x3 = (double)a[u].w;
-                    const int jc = (c0 + u) * 128;  // warp-uniform: does this 128-column chunk touch the band?
-                    if (jc <= r + kspan && jc + 127 >= r - kspan) {
-                        const int j = 4 * v;
-                        x0 *= band_weight(j, r, kd); x1 *= band_weight(j + 1, r, kd);
-                        x2 *= band_weight(j + 2, r, kd); x3 *= band_weight(j + 3, r, kd);
-                    }
-                    acc0 = fma(x0, b01.x, acc0); acc1 = fma(x1, b01.y, acc1);
-                    acc0 = fma(x2, b23.x, acc0); acc1 = fma(x3, b23.y, acc1);
-                }
-            }
-        }
-        const double acc = warp_sum(acc0 + acc1);
-        if (lane == 0) mout[r] = sb[r] * acc;
+    if (!flag_s) return;
+    __threadfence();                                       // acquire the other CTAs' marginals
+    if (threadIdx.x == 0) A.ticket[p] = 0;                 // ready for the next launch
+    double s = 0.0;
+    long long c = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double m = __ldcg(mout + j);                 // written by other SMs: bypass L1
+        if (m != 0.0) { s += m; ++c; }
     }
+    s = block_sum(s, red);
+    c = block_sum_ll(c, redll);
+    double* bw = A.bias + lo;
+    if (c == 0) {   // nothing left to balance: cooler sets bias = NaN, scale = NaN, var = 0
+        if (threadIdx.x == 0) {
+            hc_ice_result r; r.scale = __longlong_as_double(0x7ff8000000000000ll); r.var = 0.0;
+            r.iters = k; r.converged = 1;
+            A.results[p] = r; A.done[p] = 1; atomicAdd(A.n_done, 1);
+        }
+        return;
+    }
+    const double mean = s / (double)c;
+    double v = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double m = __ldcg(mout + j);
+        if (m != 0.0) { const double d = m - mean; v += d * d; }
+    }
+    const double var = block_sum(v, red) / (double)c;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double m = __ldcg(mout + j) / mean;
+        if (m == 0.0) m = 1.0;
+        bw[j] = bw[j] / m;
+    }
+    if (threadIdx.x == 0) {
+        hc_ice_result r; r.scale = mean; r.var = var; r.iters = k; r.converged = var < A.tol;
+        A.results[p] = r;
+        if (var < A.tol || k >= A.max_iters) { A.done[p] = 1; atomicAdd(A.n_done, 1); }
+    }
+}
+
+// user bias (concatenated bins) <-> padded internal layout
+__global__ void __launch_bounds__(256)
+ice_pad_bias_kernel(const int64_t* __restrict__ bin_off, const int64_t* __restrict__ pad_off, int nprob,
+                    const double* __restrict__ bias, double* __restrict__ padded) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= bin_off[nprob]) return;
+    int p = 0;
+    while (p + 1 < nprob && bin_off[p + 1] <= g) ++p;
+    padded[pad_off[p] + (g - bin_off[p])] = bias[g];
 }
 
 // final weights: bias==0 -> NaN; divide by sqrt(scale) when rescaling (cooler balance_cooler tail)
 __global__ void __launch_bounds__(256)
-ice_finalize_kernel(const int64_t* __restrict__ bin_off, int nprob, const hc_ice_result* __restrict__ results,
-                    const double* b0, const double* b1, int rescale, double* out) {  // out may alias b0
+ice_finalize_kernel(const int64_t* __restrict__ bin_off, const int64_t* __restrict__ pad_off, int nprob,
+                    const hc_ice_result* __restrict__ results, int rescale, const double* __restrict__ padded,
+                    double* __restrict__ bias) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= bin_off[nprob]) return;
     int p = 0;
     while (p + 1 < nprob && bin_off[p + 1] <= g) ++p;
     const hc_ice_result r = results[p];
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    double b = (r.iters & 1) ? b1[g] : b0[g];
+    double b = padded[pad_off[p] + (g - bin_off[p])];
     if (isnan(r.scale)) b = nan;
     else {
         if (b == 0.0) b = nan;
         if (rescale) b = b / sqrt(r.scale);
     }
-    out[g] = b;
+    bias[g] = b;
 }
+
+typedef void (*IterKernel)(IceDenseArgs, int);
+struct IterVariant { IterKernel fn; int rg, u, minb; };
+// tuned on B200 (profiles/): more rows per warp = fewer bias reads; RG*U 128-bit loads in flight per lane
+const IterVariant kVariants[] = {
+    {ice_dense_iter_kernel<2, 2, 4>, 2, 2, 4},   // default: 5.28 TB/s on C2 (profiles/r1b_ice_variants.log)
+    {ice_dense_iter_kernel<4, 2, 3>, 4, 2, 3},
+    {ice_dense_iter_kernel<2, 4, 3>, 2, 4, 3},
+    {ice_dense_iter_kernel<4, 2, 4>, 4, 2, 4},
+    {ice_dense_iter_kernel<4, 4, 2>, 4, 4, 2},
+    {ice_dense_iter_kernel<8, 2, 2>, 8, 2, 2},
+};
 
 }  // namespace
 
@@ -300,93 +338,107 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     HC_REQUIRE(P->max_iters >= 1 && P->ignore_diags >= 0, "max_iters>=1, ignore_diags>=0");
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nbins = 0;
-    int max_n = 0;
     double sum_sq = 0.0;
     for (int p = 0; p < nprob; ++p) {
         HC_REQUIRE(h_mat_n[p] >= 0, "matrix side");
         nbins += h_mat_n[p];
-        max_n = std::max(max_n, h_mat_n[p]);
         sum_sq += (double)h_mat_n[p] * (double)h_mat_n[p];
     }
     if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; }
     if (nbins == 0) return HC_OK;
 
-    // ---- launch shape: the staged bias segment decides how many CTAs fit per SM -------------
-    std::vector<int32_t> h_ld(nprob);
-    HC_CUDA(cudaMemcpyAsync(h_ld.data(), mat_ld, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
-    int ld_max = 0;
-    for (int p = 0; p < nprob; ++p) {
-        HC_REQUIRE(h_ld[p] >= h_mat_n[p] && (h_ld[p] & 3) == 0, "ld must be >= n and a multiple of 4");
-        ld_max = std::max(ld_max, h_ld[p]);
-    }
-    const size_t smem = (size_t)ld_max * sizeof(double);
-    int threads, ctas_per_sm;
-    if (smem <= 54 * 1024) { threads = 256; ctas_per_sm = 4; }
-    else if (smem <= 110 * 1024) { threads = 512; ctas_per_sm = 2; }
-    else if (smem <= 220 * 1024) { threads = 1024; ctas_per_sm = 1; }
-    else {
-        hc_set_error("hc_ice_dense_balance: matrix side %d needs %zu B of shared memory for the staged bias; "
-                     "use the CSR path for matrices this large", max_n, smem);
-        return HC_ERR_UNSUPPORTED;
-    }
-    HC_CUDA(cudaFuncSetAttribute(ice_dense_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int vi = 0;
+    if (const char* e = getenv("HC_ICE_VARIANT")) vi = atoi(e);
+    if (vi < 0 || vi >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) vi = 0;
+    const IterVariant V = kVariants[vi];
+    int waves = 2;   // CTAs per resident slot: finer row ranges balance the tail of each launch
+    if (const char* e = getenv("HC_ICE_WAVES")) waves = std::max(1, atoi(e));
 
-    // ---- static work plan: CTAs per problem proportional to n^2, contiguous row ranges -----
-    const int G = hc_num_sms() * ctas_per_sm;
-    std::vector<int32_t> cta_prob, cta_row0, cta_row1;
+    // ---- static work plan: CTAs per problem proportional to n^2; contiguous row ranges whose
+    //      length is a multiple of (8 warps x RG rows) so every warp of a CTA gets whole row groups
+    const int G = hc_num_sms() * V.minb * waves;
+    const int unit = 8 * V.rg;
+    std::vector<int32_t> cta_prob, cta_row0, cta_row1, prob_ncta(nprob, 0);
     for (int p = 0; p < nprob; ++p) {
         const int n = h_mat_n[p];
         if (n == 0) continue;
         int nc = (int)llround((double)G * ((double)n * n) / sum_sq);
-        nc = std::max(1, std::min(nc, n));
-        for (int c = 0; c < nc; ++c) {
-            cta_prob.push_back(p);
-            cta_row0.push_back((int32_t)((int64_t)n * c / nc));
-            cta_row1.push_back((int32_t)((int64_t)n * (c + 1) / nc));
+        const int units = (n + unit - 1) / unit;
+        nc = std::max(1, std::min(nc, units));
+        const int per = (units + nc - 1) / nc * unit;          // rows per CTA
+        for (int r0 = 0; r0 < n; r0 += per) {
+            cta_prob.push_back(p); cta_row0.push_back(r0); cta_row1.push_back(std::min(n, r0 + per));
+            ++prob_ncta[p];
         }
     }
     const int ncta = (int)cta_prob.size();
 
-    // scratch carved from `work` (3*nbins doubles) + a small device block for tables/flags
-    double* bias1 = work;
-    double* marg0 = work + nbins;
-    double* marg1 = work + 2 * nbins;
+    // padded internal vectors: problem p owns [pad_off[p], pad_off[p] + ld_p), 128-byte aligned, so the
+    // kernel can read the bias of any 4-column group with two aligned 16-byte loads and never
+    // needs a column bound check (matrix padding columns are zero, padded bias entries are zero)
+    std::vector<int32_t> h_ld(nprob);
+    HC_CUDA(cudaMemcpyAsync(h_ld.data(), mat_ld, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    std::vector<int64_t> h_pad(nprob + 1, 0);
+    for (int p = 0; p < nprob; ++p) {
+        if (h_ld[p] < h_mat_n[p] || (h_ld[p] & 127) != 0) {
+            hc_set_error("hc_ice_dense_balance: ld must be >= n and a multiple of 128 elements (matrix %d: n=%d ld=%d)",
+                         p, h_mat_n[p], h_ld[p]);
+            return HC_ERR_ARG;
+        }
+        h_pad[p + 1] = h_pad[p] + h_ld[p];
+    }
+    const int64_t npad = h_pad[nprob];
+    (void)work;   // scratch is allocated stream-ordered below; `work` is kept for ABI stability
+    double* d_vec = nullptr;     // [npad] bias | [npad] marg | [nprob+1] pad_off (as int64)
+    HC_CUDA(cudaMallocAsync((void**)&d_vec, (2 * (size_t)npad + nprob + 1) * sizeof(double), s));
+    double* biasp = d_vec;
+    double* marg = d_vec + npad;
+    int64_t* d_pad = reinterpret_cast<int64_t*>(d_vec + 2 * npad);
+    HC_CUDA(cudaMemsetAsync(d_vec, 0, 2 * (size_t)npad * sizeof(double), s));
+    HC_CUDA(cudaMemcpyAsync(d_pad, h_pad.data(), (nprob + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ice_pad_bias_kernel<<<(unsigned)((nbins + 255) / 256), 256, 0, s>>>(bin_off, d_pad, nprob, bias, biasp);
+    HC_LAUNCH_CHECK();
     int32_t* d_tab = nullptr;
-    const size_t tab_ints = (size_t)3 * ncta + nprob + 1;
+    const size_t tab_ints = (size_t)3 * ncta + 3 * (size_t)nprob + 1;
     HC_CUDA(cudaMallocAsync((void**)&d_tab, tab_ints * sizeof(int32_t), s));
     HC_CUDA(cudaMemcpyAsync(d_tab, cta_prob.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaMemcpyAsync(d_tab + ncta, cta_row0.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaMemcpyAsync(d_tab + 2 * ncta, cta_row1.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HC_CUDA(cudaMemsetAsync(d_tab + 3 * ncta, 0, (nprob + 1) * sizeof(int32_t), s));
+    HC_CUDA(cudaMemcpyAsync(d_tab + 3 * ncta, prob_ncta.data(), nprob * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    HC_CUDA(cudaMemsetAsync(d_tab + 3 * ncta + nprob, 0, (2 * (size_t)nprob + 1) * sizeof(int32_t), s));
 
     IceDenseArgs A;
-    A.mats = mats; A.mat_off = mat_off; A.mat_n = mat_n; A.mat_ld = mat_ld; A.bin_off = bin_off;
+    A.mats = mats; A.mat_off = mat_off; A.mat_n = mat_n; A.mat_ld = mat_ld; A.pad_off = d_pad;
     A.cta_prob = d_tab; A.cta_row0 = d_tab + ncta; A.cta_row1 = d_tab + 2 * ncta;
-    A.bias[0] = bias; A.bias[1] = bias1; A.marg[0] = marg0; A.marg[1] = marg1;
-    A.results = results; A.done = d_tab + 3 * ncta; A.n_done = d_tab + 3 * ncta + nprob;
+    A.prob_ncta = d_tab + 3 * ncta;
+    A.ticket = d_tab + 3 * ncta + nprob;
+    A.done = d_tab + 3 * ncta + 2 * nprob;
+    A.n_done = d_tab + 3 * ncta + 3 * nprob;
+    A.bias = biasp; A.marg = marg; A.results = results;
     A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters;
 
     int nonempty = 0;
     for (int p = 0; p < nprob; ++p) nonempty += h_mat_n[p] > 0;
-    // empty problems never get a CTA: give them a defined result
-    if (nonempty != nprob) {
+    if (nonempty != nprob) {   // empty problems never get a CTA: give them a defined result
         std::vector<hc_ice_result> h_res(nprob);
         for (int p = 0; p < nprob; ++p) { h_res[p].scale = NAN; h_res[p].var = 0.0; h_res[p].iters = 0; h_res[p].converged = 1; }
         HC_CUDA(cudaMemcpyAsync(results, h_res.data(), sizeof(hc_ice_result) * nprob, cudaMemcpyHostToDevice, s));
         HC_CUDA(cudaStreamSynchronize(s));
     }
+    // the bias vector is the only data that should live in L1: no shared-memory carve-out
+    cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
 
     const int poll = P->poll_every > 0 ? P->poll_every : 8;
     int launches = 0, h_done = 0;
     int rc = HC_OK;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the iteration loop, for the roofline
     if (h_info) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, s); }
-    for (int k = 1; k <= P->max_iters + 1; ++k) {
-        ice_dense_iter_kernel<<<ncta, threads, smem, s>>>(A, k);
+    for (int k = 1; k <= P->max_iters; ++k) {
+        V.fn<<<ncta, 256, 0, s>>>(A, k);
         hc_count_launch();
         ++launches;
-        if (k % poll == 0 || k == P->max_iters + 1) {
+        if (k % poll == 0 || k == P->max_iters) {
             cudaError_t e = cudaMemcpyAsync(&h_done, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
@@ -396,14 +448,14 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     if (h_info && ev0) cudaEventRecord(ev1, s);
     if (rc == HC_OK) {
         const int64_t blocks = (nbins + 255) / 256;
-        ice_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin_off, nprob, results, bias, bias1,
-                                                             P->rescale_marginals, bias);
+        ice_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin_off, d_pad, nprob, results, P->rescale_marginals, biasp, bias);
         hc_count_launch();
         ++launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; }
     }
     cudaFreeAsync(d_tab, s);
+    cudaFreeAsync(d_vec, s);
     cudaError_t e = cudaStreamSynchronize(s);  // host tables above must outlive the copies
     if (rc == HC_OK && e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; }
     if (h_info) {

@@ -1,0 +1,228 @@
+// Hand-written LSD radix sort (64-bit keys, keys only) in the "onesweep" style: one upfront
+// histogram pass over all digits, then ONE kernel per 8-bit digit that ranks a tile in shared
+// memory and resolves its global offsets with a decoupled look-back over earlier tiles -- every
+// key is read once and written once per pass.  This is the sort of north_star kernel (a)
+// ("radix sort plus reduce-by-key"); the keys are row*nbins+col bin pairs built by hc_csr.cu.
+//
+// Roofline: HBM-bound, 8*P (histogram) + passes*16*P bytes for P keys.
+#include "hc_common.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys = 32 KB
+constexpr int MAX_PASSES = 8;
+
+constexpr unsigned long long FLAG_AGG = 1ull << 62;
+constexpr unsigned long long FLAG_INC = 2ull << 62;
+constexpr unsigned long long FLAG_MASK = 3ull << 62;
+
+// ---- upfront histogram of every digit --------------------------------------------------
+__global__ void __launch_bounds__(512)
+radix_histogram_kernel(const unsigned long long* __restrict__ keys, long long n, int begin_bit, int passes,
+                       unsigned long long* __restrict__ ghist /*[passes][256]*/) {
+    __shared__ unsigned int sh[MAX_PASSES][RADIX];
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // bounded trip count per block keeps the 32-bit shared counters from overflowing
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long k = keys[i] >> begin_bit;
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p)
+            if (p < passes) atomicAdd(&sh[p][(k >> (RADIX_BITS * p)) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
+        const unsigned int v = (&sh[0][0])[i];
+        if (v) atomicAdd(&ghist[i], (unsigned long long)v);
+    }
+}
+
+// exclusive scan of each pass's 256-bin histogram (one block per pass, 256 threads)
+__global__ void __launch_bounds__(RADIX) radix_scan_kernel(unsigned long long* __restrict__ ghist) {
+    __shared__ unsigned long long s[RADIX];
+    unsigned long long* h = ghist + (size_t)blockIdx.x * RADIX;
+    s[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int d = 0; d < RADIX; ++d) { const unsigned long long c = s[d]; s[d] = run; run += c; }
+    }
+    __syncthreads();
+    h[threadIdx.x] = s[threadIdx.x];
+}
+
+// ---- one digit pass -------------------------------------------------------------------
+struct SortSmem {
+    unsigned long long keys[SORT_TILE];
+    unsigned int warp_hist[SORT_WARPS][RADIX];
+    unsigned int tile_off[RADIX];       // exclusive scan of the tile's digit totals
+    unsigned long long gbase[RADIX];    // global position of the tile's first key of each digit
+    unsigned int scan_tmp[SORT_WARPS];
+    unsigned int tile_id;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
+                      int shift, const unsigned long long* __restrict__ digit_base /*[256]*/,
+                      unsigned long long* status /*[num_tiles][256]*/, unsigned int* tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) sm.tile_id = atomicAdd(tile_counter, 1u);   // tiles are claimed in launch order
+    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const long long tile = sm.tile_id;
+    const long long base = tile * SORT_TILE;
+    const int valid = (int)min((long long)SORT_TILE, n - base);
+
+    // warp-striped load keeps memory order == (warp, item, lane) order -> stable ranking
+    unsigned long long key[SORT_ITEMS];
+    unsigned int rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
+        key[i] = j < valid ? in[base + j] : ~0ull;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
+        const bool ok = j < valid;
+        // padding lanes get a private pseudo-digit so they match nobody and count nowhere
+        const unsigned d = ok ? (unsigned)((key[i] >> shift) & (RADIX - 1)) : (unsigned)(RADIX + lane);
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        unsigned prev = 0;
+        if (ok && lane == leader) {
+            prev = sm.warp_hist[w][d];
+            sm.warp_hist[w][d] = prev + __popc(m);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[i] = prev + __popc(m & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit (thread d): exclusive scan over warps, tile total
+    unsigned total;
+    {
+        unsigned run = 0;
+#pragma unroll
+        for (int ww = 0; ww < SORT_WARPS; ++ww) {
+            const unsigned c = sm.warp_hist[ww][tid];
+            sm.warp_hist[ww][tid] = run;
+            run += c;
+        }
+        total = run;
+    }
+    // decoupled look-back for digit `tid`
+    {
+        unsigned long long* my = status + tile * RADIX + tid;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_INC | total;
+        } else {
+            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_AGG | total;
+            long long t = tile - 1;
+            while (true) {
+                const volatile unsigned long long* p = status + t * RADIX + tid;
+                unsigned long long v;
+                do { v = *p; } while ((v & FLAG_MASK) == 0);
+                excl += v & ~FLAG_MASK;
+                if ((v & FLAG_MASK) == FLAG_INC) break;
+                --t;
+            }
+            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_INC | (excl + total);
+        }
+        sm.gbase[tid] = digit_base[tid] + excl;
+    }
+    // block exclusive scan of the digit totals -> position of each digit run inside the tile
+    {
+        unsigned incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) sm.scan_tmp[w] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int ww = 0; ww < w; ++ww) woff += sm.scan_tmp[ww];
+        sm.tile_off[tid] = woff + incl - total;
+    }
+    __syncthreads();
+
+    // reorder inside shared memory so the global writes are contiguous per digit run
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
+        if (j < valid) {
+            const unsigned d = (unsigned)((key[i] >> shift) & (RADIX - 1));
+            sm.keys[sm.tile_off[d] + sm.warp_hist[w][d] + rank[i]] = key[i];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < valid; j += SORT_THREADS) {
+        const unsigned long long k = sm.keys[j];
+        const unsigned d = (unsigned)((k >> shift) & (RADIX - 1));
+        out[sm.gbase[d] + (unsigned)(j - sm.tile_off[d])] = k;
+    }
+}
+
+}  // namespace
+
+// Workspace layout (bytes): [passes*256 u64 histogram][num_tiles*256 u64 status][16 B counters]
+extern "C" int64_t hc_sort_work_bytes(int64_t n) {
+    const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    return (int64_t)sizeof(unsigned long long) * (MAX_PASSES * RADIX + (tiles > 0 ? tiles : 1) * RADIX) + 64;
+}
+
+// Sorts keys[0..n) ascending on bits [begin_bit, end_bit).  `keys` and `tmp` are n-element
+// device buffers used as a ping-pong pair; *h_result_in_tmp tells the caller where the sorted
+// keys ended up (1 = tmp).  Stream-ordered; no host synchronisation.
+extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tmp, int64_t n, int32_t begin_bit,
+                                int32_t end_bit, void* work, int32_t* h_result_in_tmp, void* stream) {
+    HC_REQUIRE(n >= 0 && begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, "n>=0, 0<=begin<=end<=64");
+    if (h_result_in_tmp) *h_result_in_tmp = 0;
+    const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (n <= 1 || passes == 0) return HC_OK;
+    HC_REQUIRE(passes <= MAX_PASSES, "too many digit passes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    unsigned long long* ghist = reinterpret_cast<unsigned long long*>(work);
+    unsigned long long* status = ghist + MAX_PASSES * RADIX;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(status + tiles * RADIX);
+
+    HC_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * MAX_PASSES * RADIX, s));
+    {
+        long long blocks = (n + 512 * 64 - 1) / (512 * 64);     // >= 64 keys per thread
+        const long long cap = (long long)hc_num_sms() * 4;
+        if (blocks > cap) blocks = cap;
+        // 32-bit shared counters: a block sees at most n/blocks keys; split further if needed
+        while (n / blocks >= (1ll << 31)) blocks *= 2;
+        radix_histogram_kernel<<<(unsigned)blocks, 512, 0, s>>>(keys, n, begin_bit, passes, ghist);
+        HC_LAUNCH_CHECK();
+    }
+    radix_scan_kernel<<<passes, RADIX, 0, s>>>(ghist);
+    HC_LAUNCH_CHECK();
+
+    const size_t smem = sizeof(SortSmem);
+    HC_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned long long* src = keys;
+    unsigned long long* dst = tmp;
+    for (int p = 0; p < passes; ++p) {
+        HC_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned long long) * tiles * RADIX + 16, s));
+        radix_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, smem, s>>>(
+            src, dst, n, begin_bit + RADIX_BITS * p, ghist + p * RADIX, status, counter);
+        HC_LAUNCH_CHECK();
+        unsigned long long* t = src; src = dst; dst = t;
+    }
+    if (h_result_in_tmp) *h_result_in_tmp = (src == tmp) ? 1 : 0;
+    return HC_OK;
+}

@@ -10,7 +10,7 @@ import torch
 
 from . import _abi
 
-ROW_ALIGN = 32  # int32 elements -> 128-byte rows (vector loads need a multiple of 4)
+ROW_ALIGN = 128  # int32 elements -> 512-byte rows: every 128-column chunk a warp streams is full
 
 
 def require_cuda(device=None) -> torch.device:

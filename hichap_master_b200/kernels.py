@@ -79,6 +79,49 @@ def dense_nonzero_records(base_ptr: int, ld: int, nrows: int, ncols: int, triu: 
     return rec
 
 
+class PinnedPool:
+    """Grow-only pinned host buffer + device staging buffer reused across calls (pinned
+    allocation is far too slow to repeat per call)."""
+
+    def __init__(self):
+        self.host = None
+        self.dev = None
+
+    def get(self, nbytes: int, device):
+        if self.host is None or self.host.numel() < nbytes:
+            cap = int(nbytes * 1.25) + 4096
+            self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self.dev = torch.empty(cap, dtype=torch.uint8, device=device)
+        return self.host, self.dev
+
+
+_RECORD_POOL = PinnedPool()
+
+
+def dense_batch_triu_records(batch: DenseBatch, pool: PinnedPool = None):
+    """Upper-triangular records of EVERY matrix of the batch in the reference's structured
+    layout (matrixBuilding.py:508-524), produced on the device and copied to the host once.
+    Returns a list (one per matrix) of S_DTYPE arrays that are views of one pinned buffer --
+    valid until the next call with the same pool."""
+    pool = _RECORD_POOL if pool is None else pool
+    dev, n = batch.device, batch.nbins
+    row_ptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    check(lib().hc_dense_batch_triu_count(ptr(batch.buf), ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld),
+                                          ptr(batch.bin_off), len(batch), n, ptr(row_ptr), stream_ptr()),
+          "hc_dense_batch_triu_count")
+    bounds = row_ptr[batch.bin_off].cpu().numpy()          # one small D2H: record range per matrix
+    total = int(bounds[-1])
+    host, dbuf = pool.get(24 * max(total, 1), dev)
+    if total:
+        check(lib().hc_dense_batch_triu_records(ptr(batch.buf), ptr(batch.mat_off), ptr(batch.mat_n),
+                                                ptr(batch.mat_ld), ptr(batch.bin_off), len(batch), n, ptr(row_ptr),
+                                                ptr(dbuf), stream_ptr()), "hc_dense_batch_triu_records")
+        host[:24 * total].copy_(dbuf[:24 * total], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    rec = host[:24 * total].numpy().view(S_DTYPE)
+    return [rec[int(bounds[i]):int(bounds[i + 1])] for i in range(len(batch))], 24 * total
+
+
 # --------------------------------------------------------------------------------------
 # (b) ICE
 # --------------------------------------------------------------------------------------
@@ -182,3 +225,153 @@ def twostep_correct(x_ptr: int, ld: int, n: int, alpha, gapflag, has_gap: bool, 
                                    ptr(rowsum_x), ptr(out), out.stride(0), ptr(work), stream_ptr()),
           "hc_twostep_correct")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# (a') sort path: pairs -> keys -> radix sort -> reduce-by-key -> symmetric CSR
+# --------------------------------------------------------------------------------------
+def sort_keys_u64(keys, nbits: int, tmp=None):
+    """Ascending radix sort of a uint64 device tensor (viewed as int64 by torch) on its low
+    ``nbits`` bits.  Returns the sorted tensor (one of ``keys`` / ``tmp``)."""
+    n = int(keys.numel())
+    if tmp is None:
+        tmp = torch.empty_like(keys)
+    work = torch.empty(int(lib().hc_sort_work_bytes(n)), dtype=torch.uint8, device=keys.device)
+    in_tmp = C.c_int32(0)
+    check(lib().hc_sort_keys_u64(ptr(keys), ptr(tmp), n, 0, int(nbits), ptr(work), C.byref(in_tmp), stream_ptr()),
+          "hc_sort_keys_u64")
+    return (tmp, keys) if in_tmp.value else (keys, tmp)
+
+
+class SymCsr:
+    """Symmetric CSR of one contact matrix over ``nbins`` concatenated bins (both triangles
+    stored); ``row0`` / ``nloc`` describe the row block held locally (all rows on one GPU)."""
+
+    def __init__(self, row_ptr, col, cnt, nbins, row0=0):
+        self.row_ptr, self.col, self.cnt = row_ptr, col, cnt
+        self.nbins, self.row0 = int(nbins), int(row0)
+        self.nloc = int(row_ptr.numel()) - 1
+        self.nnz = int(col.numel())
+        self.device = col.device
+
+
+def keys_to_csr(sorted_keys, n_valid, col_bits: int, nrows: int, scratch=None):
+    """Reduce-by-key over sorted keys -> (row_ptr int64[nrows+1], col int32, cnt int32)."""
+    dev, nkeys = sorted_keys.device, int(sorted_keys.numel())
+    work = torch.empty(int(lib().hc_csr_work_bytes(nkeys)), dtype=torch.uint8, device=dev)
+    nnz = C.c_int64(0)
+    check(lib().hc_csr_count(ptr(sorted_keys), nkeys, ptr(n_valid), ptr(work), C.byref(nnz), stream_ptr()),
+          "hc_csr_count")
+    nnz = int(nnz.value)
+    row_ptr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    cnt = torch.empty(nnz, dtype=torch.int32, device=dev)
+    ukey = scratch if (scratch is not None and scratch.numel() >= nnz) else torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
+    upos = torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
+    check(lib().hc_csr_emit(ptr(sorted_keys), nkeys, ptr(n_valid), ptr(work), nnz, int(col_bits), int(nrows),
+                            ptr(ukey), ptr(upos), ptr(row_ptr), ptr(col), ptr(cnt), stream_ptr()), "hc_csr_emit")
+    return row_ptr, col, cnt
+
+
+def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                 check_bounds=True) -> SymCsr:
+    """Binning through the sort path (north_star kernel (a)): every pair becomes one or two
+    (row, col) keys, the keys are radix-sorted and run-length reduced into a symmetric CSR."""
+    dev = pairs.device
+    col_bits = max(1, int(nbins - 1).bit_length())
+    keys = torch.empty(2 * max(pairs.n, 1), dtype=torch.int64, device=dev)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+    oob = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().hc_pairs_to_keys(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2), pairs.n, int(res),
+                                 ptr(start), ptr(chrom_bins), int(start.numel()), int(bool(cis_only)), col_bits,
+                                 ptr(keys), ptr(n_valid), ptr(oob), stream_ptr()), "hc_pairs_to_keys")
+    if check_bounds:
+        _raise_oob(oob, "genome-wide")
+    keys = keys[:2 * pairs.n]
+    # padding keys are ~0: they sort last on every digit, so sorting the low 2*col_bits bits
+    # (rounded up to whole 8-bit digits) leaves the real keys first and in order
+    skeys, free = sort_keys_u64(keys, 2 * col_bits) if pairs.n else (keys, None)
+    row_ptr, col, cnt = keys_to_csr(skeys, n_valid, col_bits, nbins, scratch=free)
+    return SymCsr(row_ptr, col, cnt, nbins)
+
+
+def csr_upper_records(csr: SymCsr):
+    """Upper-triangular (bin1, bin2, count) int32 device tensors of the local rows, row-major
+    (bin1 is LOCAL to the row block; add csr.row0 for global bins)."""
+    dev = csr.device
+    out_ptr = torch.empty(csr.nloc + 1, dtype=torch.int64, device=dev)
+    check(lib().hc_csr_upper_count(ptr(csr.row_ptr), ptr(csr.col), csr.nloc, ptr(out_ptr), stream_ptr()),
+          "hc_csr_upper_count")
+    n = int(out_ptr[-1].item())
+    b1 = torch.empty(n, dtype=torch.int32, device=dev)
+    b2 = torch.empty(n, dtype=torch.int32, device=dev)
+    v = torch.empty(n, dtype=torch.int32, device=dev)
+    if n:
+        check(lib().hc_csr_upper_emit(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.nloc, ptr(out_ptr),
+                                      ptr(b1), ptr(b2), ptr(v), stream_ptr()), "hc_csr_upper_emit")
+    return b1, b2, v
+
+
+def ice_balance_csr(csr: SymCsr, prob_off, chrom_off=None, comm=None, allreduce=None, **kw):
+    """ICE on the symmetric CSR.  ``prob_off``: host int64 array of problem boundaries over the
+    bins ([0, nbins] = genome-wide; per-chromosome offsets on cis-only keys = --cis-only).
+    ``chrom_off``: chromosome boundaries for the MAD-max filter (defaults to prob_off).
+    Row-block sharding: ``comm`` = handle from nccl_comm_init (in-loop allreduce) and
+    ``allreduce`` = callable used for the two filter vectors (torch.distributed.all_reduce)."""
+    params = ice_params(**kw)
+    dev, n = csr.device, csr.nbins
+    prob_off = np.ascontiguousarray(prob_off, dtype=np.int64)
+    chrom_off = prob_off if chrom_off is None else np.ascontiguousarray(chrom_off, dtype=np.int64)
+    d_prob = torch.from_numpy(prob_off).to(dev)
+    d_chrom = torch.from_numpy(chrom_off).to(dev)
+    nnz_marg = torch.zeros(n, dtype=torch.float64, device=dev)
+    marg = torch.zeros(n, dtype=torch.float64, device=dev)
+    check(lib().hc_ice_csr_marginals(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.row0, csr.nloc,
+                                     params.ignore_diags, ptr(nnz_marg), ptr(marg), stream_ptr()),
+          "hc_ice_csr_marginals")
+    if allreduce is not None:
+        allreduce(nnz_marg)
+        allreduce(marg)
+    bias = torch.empty(n, dtype=torch.float64, device=dev)
+    fwork = torch.empty(2 * max(n, 1), dtype=torch.float64, device=dev)
+    check(lib().hc_ice_filter_bins(ptr(nnz_marg), ptr(marg), n, ptr(d_chrom), len(chrom_off) - 1,
+                                   C.byref(params), ptr(bias), ptr(fwork), stream_ptr()), "hc_ice_filter_bins")
+    nprob = len(prob_off) - 1
+    work = torch.empty(int(lib().hc_ice_csr_work_bytes(n, nprob)), dtype=torch.uint8, device=dev)
+    res = torch.zeros(nprob * C.sizeof(IceResult), dtype=torch.uint8, device=dev)
+    info = IceRunInfo(0, 0.0)
+    h_off = (C.c_int64 * len(prob_off))(*[int(x) for x in prob_off])
+    check(lib().hc_ice_csr_balance(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.row0, csr.nloc, ptr(d_prob),
+                                   nprob, h_off, C.byref(params), ptr(bias), ptr(work), ptr(res), C.byref(info),
+                                   C.c_void_p(comm or 0), stream_ptr()), "hc_ice_csr_balance")
+    rdt = np.dtype([("scale", "<f8"), ("var", "<f8"), ("iters", "<i4"), ("converged", "<i4")])
+    results = res.cpu().numpy().view(rdt)
+    stats = dict(tol=params.tol, min_nnz=params.min_nnz, min_count=params.min_count, mad_max=params.mad_max,
+                 cis_only=nprob > 1, ignore_diags=params.ignore_diags, divisive_weights=False,
+                 launches=int(info.launches), loop_ms=float(info.loop_ms))
+    if nprob == 1:
+        stats.update(scale=float(results["scale"][0]), var=float(results["var"][0]),
+                     converged=bool(results["converged"][0]), iters=int(results["iters"][0]))
+    else:
+        stats.update(scale=results["scale"].copy(), var=float(results["var"][-1]),
+                     converged=bool(results["var"][-1] < params.tol), iters=[int(i) for i in results["iters"]],
+                     converged_per_chrom=[bool(c) for c in results["converged"]])
+    return bias, stats
+
+
+# ---- NCCL communicator for the row-block sharded ICE -------------------------------------
+def nccl_unique_id() -> bytes:
+    buf = (C.c_char * 128)()
+    check(lib().hc_nccl_unique_id(buf), "hc_nccl_unique_id")
+    return bytes(buf)
+
+
+def nccl_comm_init(uid: bytes, nranks: int, rank: int) -> int:
+    comm = C.c_void_p(0)
+    buf = (C.c_char * 128).from_buffer_copy(uid)
+    check(lib().hc_nccl_comm_init(buf, nranks, rank, C.byref(comm)), "hc_nccl_comm_init")
+    return int(comm.value)
+
+
+def nccl_comm_destroy(comm: int):
+    check(lib().hc_nccl_comm_destroy(C.c_void_p(comm)), "hc_nccl_comm_destroy")

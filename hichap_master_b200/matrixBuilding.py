@@ -171,8 +171,10 @@ def TraditionalMatrixBuilding(bed_IO, genomeSize, wholeRes, localRes, chroms):
     pairs = _to_pair_columns(bed_IO, order, chroms, "valid23", dev)
     whole, local = bin_traditional(pairs, genome, wholeRes, localRes, dev)
     Whole_Lib = {res: WholeMatrixToSparseDict(bins, W) for res, (bins, W) in whole.items()}
-    Local_Lib = {res: IntraMatrixToSparseDict({c: (L, i) for i, c in enumerate(order)})
-                 for res, L in local.items()}
+    Local_Lib = {}
+    for res, L in local.items():
+        recs, _ = kernels.dense_batch_triu_records(L)
+        Local_Lib[res] = {c: recs[i].copy() for i, c in enumerate(order)}   # own the memory (pool is reused)
     return Whole_Lib, Local_Lib
 
 
@@ -290,3 +292,62 @@ def ice_balance_dense(mats, chrom_offsets=None, ignore_diags=1, mad_max=5, min_n
     return kernels.ice_balance_dense(batch, off, ignore_diags=ignore_diags, mad_max=mad_max,
                                      min_nnz=min_nnz, min_count=min_count, tol=tol, max_iters=max_iters,
                                      rescale_marginals=rescale_marginals)
+
+
+# ======================================================================================
+# sort path (genome-wide matrices that do not fit dense tiles): pairs -> symmetric CSR
+# ======================================================================================
+def bin_traditional_sparse(pairs: PairColumns, genome: dict, res: int, cis_only=False, device=None):
+    """Genome-wide binning through radix sort + reduce-by-key (north_star kernel (a)).
+    Same bins as ``Get_Chro_Bins`` (matrixBuilding.py:409-426).  Returns (Bins, SymCsr)."""
+    dev = require_cuda(device)
+    order = Sort_Chromosomes(genome)
+    bins, total = _bins_from_genome(genome, res, [(c, c) for c in order])
+    start = _start_table(bins, order, dev)
+    chrom_bins = torch.tensor([genome[c] // res + 1 for c in order], dtype=torch.int32, device=dev)
+    return bins, kernels.pairs_to_csr(pairs, res, start, chrom_bins, total, cis_only)
+
+
+def chrom_offsets_from_bins(Bins):
+    """nchrom+1 bin offsets in ``Sort_Chromosomes`` order (the cool file's indexes/chrom_offset)."""
+    order = Sort_Chromosomes(Bins.keys())
+    return np.array([Bins[c][0] for c in order] + [Bins[order[-1]][1] + 1], dtype=np.int64)
+
+
+def WholeCsrToSparseDict(Bins, csr):
+    """``WholeMatrixToSparseDict`` (matrixBuilding.py:457-506) for a genome-wide symmetric CSR:
+    intra blocks keyed 'c' (upper triangle), inter blocks 'c1_c2' (c1 before c2), block-local
+    coordinates, row-major order inside each block."""
+    b1, b2, v = (t.cpu().numpy() for t in kernels.csr_upper_records(csr))
+    b1 = b1.astype(np.int64) + csr.row0
+    order = Sort_Chromosomes(Bins.keys())
+    off = chrom_offsets_from_bins(Bins)
+    ca = np.searchsorted(off, b1, side="right") - 1
+    cb = np.searchsorted(off, b2, side="right") - 1
+    out = {}
+    # upper-triangular pixels have chrom(bin1) <= chrom(bin2); group by (ca, cb) preserving order
+    grp = ca * len(order) + cb
+    idx = np.argsort(grp, kind="stable")
+    bounds = np.searchsorted(grp[idx], np.arange(len(order) * len(order) + 1))
+    for i, c1 in enumerate(order):
+        for j in range(i, len(order)):
+            c2 = order[j]
+            sel = idx[bounds[i * len(order) + j]:bounds[i * len(order) + j + 1]]
+            rec = np.zeros(sel.size, dtype=S_dtype)
+            rec["bin1"], rec["bin2"], rec["IF"] = b1[sel] - off[i], b2[sel].astype(np.int64) - off[j], v[sel]
+            out[c1 if i == j else c1 + "_" + c2] = rec
+    return out
+
+
+def ice_balance_sparse(csr, Bins, cis_only=False, ignore_diags=1, mad_max=5, min_nnz=10, min_count=0,
+                       tol=1e-5, max_iters=200, rescale_marginals=True, comm=None, allreduce=None):
+    """`cooler balance --ignore-diags K [--cis-only]` on the symmetric CSR.  With ``cis_only``
+    the CSR must have been built from cis pairs only (``bin_traditional_sparse(cis_only=True)``):
+    every chromosome then iterates on its own."""
+    off = chrom_offsets_from_bins(Bins)
+    prob = off if cis_only else np.array([0, off[-1]], dtype=np.int64)
+    bias, stats = kernels.ice_balance_csr(csr, prob, chrom_off=off, comm=comm, allreduce=allreduce,
+                                          ignore_diags=ignore_diags, mad_max=mad_max, min_nnz=min_nnz,
+                                          min_count=min_count, tol=tol, max_iters=max_iters,
+                                          rescale_marginals=rescale_marginals)
+    return bias.cpu().numpy(), stats

@@ -37,6 +37,7 @@ class LocalStage:
         self.max_pairs = int(max_pairs)
         self.cols = [torch.empty(max(self.max_pairs, 4), dtype=torch.int32, device=self.dev) for _ in range(4)]
         self.weights_host = torch.empty(self.batch.nbins, dtype=torch.float64).pin_memory()
+        self.pool = kernels.PinnedPool()
 
     def upload(self, hp: HostPairs) -> PairColumns:
         assert hp.n <= self.max_pairs
@@ -52,12 +53,8 @@ class LocalStage:
         recs = None
         d2h = 0
         if records:
-            recs = []
-            for i in range(len(b)):
-                r = kernels.dense_nonzero_records(b.buf.data_ptr() + 4 * b.offsets[i], b.lds[i], b.sizes[i],
-                                                  b.sizes[i], True, False, b.dev if hasattr(b, "dev") else b.device)
-                recs.append(r)
-                d2h += 12 * r.size
+            recs, nbytes = kernels.dense_batch_triu_records(b, self.pool)
+            d2h += nbytes
         params = kernels.ice_params(**ice_kw)
         bias = kernels.ice_dense_filters(b, params)
         results, info = kernels.ice_dense_iterate(b, bias, params)

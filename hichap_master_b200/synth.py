@@ -46,7 +46,7 @@ def cis_pairs(chrom: str, length: int, n: int, seed: int):
     bias = _bias_track(rng, length)
     bmax = bias.max()
     h0, h1 = hole(chrom, length)
-    out1, out2, have = [], [], 0
+    out1, out2, have = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)], 0
     while have < n:
         m = int((n - have) * 2.2) + 1024
         p1 = rng.integers(0, length, size=m)

@@ -82,6 +82,17 @@ int hc_dense_nonzero_extract(const void* M, int64_t ld, int32_t nrows, int32_t n
                              int32_t is_f64, const int64_t* row_ptr, int32_t* bin1, int32_t* bin2,
                              void* val, void* stream);
 
+/* The same marshalling for EVERY matrix of a dense batch in two launches, producing the
+ * reference's record layout directly: records[i] = {int64 bin1, int64 bin2, float64 IF} (24 B,
+ * the S_dtype of matrixBuilding.py:460-461), upper triangle, row-major; the records of matrix p
+ * are the contiguous range [row_ptr[bin_off[p]], row_ptr[bin_off[p+1]]).  row_ptr: nbins+1. */
+int hc_dense_batch_triu_count(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                              const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                              int64_t nbins, int64_t* row_ptr, void* stream);
+int hc_dense_batch_triu_records(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
+                                int64_t nbins, const int64_t* row_ptr, void* records, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b) ICE balancing == `cooler balance --ignore-diags K [--cis-only]`
  * (call sites matrixBuilding.py:708, :713, :1537, :1542, :1761, :1766; arithmetic restated in
@@ -133,15 +144,81 @@ typedef struct hc_ice_run_info {
  * bias: in = initial bias from the filters, out = final weights (NaN for masked bins, divided
  * by sqrt(scale) when rescale_marginals).  work: 3*nbins doubles.  The reduction over the
  * marginals, the bias update, the rescale and the convergence test all run on the device
- * inside the same kernel that streams the matrix; the host only polls a done counter. */
+ * inside the same kernel that streams the matrix; the host only polls a done counter.
+ * Every mat_ld must be a multiple of 128 elements (512-byte rows). */
 int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
                          const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
                          const int32_t* h_mat_n, const hc_ice_params* h_params, double* bias,
                          double* work, hc_ice_result* results, hc_ice_run_info* h_info, void* stream);
 
-/* Upper-triangular CSR variant (genome-wide matrices too large for dense tiles): one problem,
- * rows [row_lo,row_hi) held by this rank (row-block sharding), full-length bias.  See csr.h
- * section below. */
+/* ------------------------------------------------------------------------------------------
+ * (a') Sort path: pairs -> keys -> radix sort -> reduce-by-key -> SYMMETRIC CSR (both triangles
+ * stored) with integer counts.  Replaces the dense accumulation of matrixBuilding.py:559-603
+ * where the dense matrix is infeasible (genome-wide 10 kb / 5 kb).  The reference's
+ * upper-triangular records (matrixBuilding.py:489-503) are the col >= row subset.
+ * ---------------------------------------------------------------------------------------- */
+
+/* key = (row << col_bits) | col with row/col = pos/res + start[chrom]; every off-diagonal pair
+ * yields two keys (row,col) and (col,row), a diagonal pair one; dropped pairs (filtered
+ * chromosome, or trans when cis_only) yield the padding key ~0.  keys: 2*npairs entries.
+ * *n_valid (device) receives the number of real keys; *oob counts out-of-range pairs.
+ * start: device int64[nchrom]; chrom_bins: device int32[nchrom] (bins per chromosome). */
+int hc_pairs_to_keys(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                     int64_t npairs, int32_t res, const int64_t* start, const int32_t* chrom_bins,
+                     int32_t nchrom, int32_t cis_only, int32_t col_bits, unsigned long long* keys,
+                     unsigned long long* n_valid, unsigned long long* oob, void* stream);
+
+/* LSD radix sort of 64-bit keys on bits [begin_bit, end_bit), 8 bits per pass, onesweep style
+ * (one histogram pass + one read/write of the keys per digit, decoupled look-back).
+ * keys/tmp: n-element ping-pong buffers; *h_result_in_tmp = 1 when the sorted keys are in tmp.
+ * work: hc_sort_work_bytes(n) bytes.  Stream-ordered, no host synchronisation. */
+int64_t hc_sort_work_bytes(int64_t n);
+int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tmp, int64_t n, int32_t begin_bit,
+                     int32_t end_bit, void* work, int32_t* h_result_in_tmp, void* stream);
+
+/* Reduce-by-key over the sorted keys: count distinct keys among the first *n_valid (device)
+ * -> *h_nnz (synchronises the stream), then emit row_ptr[nrows+1], col[nnz], cnt[nnz].
+ * work: hc_csr_work_bytes(nkeys) (kept between the two calls); ukey/upos: nnz-element scratch. */
+int64_t hc_csr_work_bytes(int64_t nkeys);
+int hc_csr_count(const unsigned long long* sorted_keys, int64_t nkeys, const unsigned long long* n_valid,
+                 void* work, int64_t* h_nnz, void* stream);
+int hc_csr_emit(const unsigned long long* sorted_keys, int64_t nkeys, const unsigned long long* n_valid,
+                const void* work, int64_t nnz, int32_t col_bits, int64_t nrows, unsigned long long* ukey,
+                int64_t* upos, int64_t* row_ptr, int32_t* col, int32_t* cnt, void* stream);
+
+/* Upper-triangular (bin1, bin2, count) records of the symmetric CSR in row-major order
+ * (WholeMatrixToSparseDict's output layout before the per-chromosome split): count fills
+ * out_ptr[nrows+1] (exclusive scan), then emit. */
+int hc_csr_upper_count(const int64_t* row_ptr, const int32_t* col, int64_t nrows, int64_t* out_ptr,
+                       void* stream);
+int hc_csr_upper_emit(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t nrows,
+                      const int64_t* out_ptr, int32_t* bin1, int32_t* bin2, int32_t* val, void* stream);
+
+/* ICE on the symmetric CSR.  The local rows [row0, row0+nloc) may be a row block of a matrix
+ * sharded over several GPUs; marg / nnz_marg / bias are FULL-length vectors.
+ * hc_ice_csr_marginals writes the filter marginals of the local rows at their global positions
+ * (zero the vectors first when they will be allreduced). */
+int hc_ice_csr_marginals(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t row0,
+                         int64_t nloc, int32_t ignore_diags, double* nnz_marg, double* marg,
+                         void* stream);
+
+/* Balance to convergence (one problem per [bin_off[p], bin_off[p+1]) range: one range =
+ * genome-wide; per-chromosome ranges on cis-only keys = `--cis-only`).  bias: in = initial
+ * bias from hc_ice_filter_bins, out = final weights.  nccl_comm: NULL on one GPU, otherwise a
+ * communicator from hc_nccl_comm_init -- the marginal vector is then allreduced in-stream once
+ * per iteration and every rank applies the same O(n) update.  work: hc_ice_csr_work_bytes. */
+int64_t hc_ice_csr_work_bytes(int64_t nbins, int32_t nprob);
+int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t row0,
+                       int64_t nloc, const int64_t* bin_off, int32_t nprob, const int64_t* h_bin_off,
+                       const hc_ice_params* h_params, double* bias, void* work, hc_ice_result* results,
+                       hc_ice_run_info* h_info, void* nccl_comm, void* stream);
+
+/* NCCL plumbing (libnccl.so.2 resolved with dlopen at first use). h_id128: 128-byte host buffer. */
+int hc_nccl_available(void);
+int hc_nccl_unique_id(void* h_id128);
+int hc_nccl_comm_init(const void* h_id128, int32_t nranks, int32_t rank, void** h_comm);
+int hc_nccl_comm_destroy(void* comm);
+int hc_nccl_allreduce_sum_f64(void* comm, double* buf, int64_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (c) Two-step allelic correction (matrixBuilding.py:984-1023 TwoStepCorrection, with
