@@ -41,9 +41,13 @@ _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 # name -> (restype, argtypes); mirrors include/hichap_b200.h one to one
 SIGNATURES = {
     "hc_version": (C.c_int, []),
+    "hc_init": (C.c_int, []),
     "hc_last_error": (C.c_char_p, []),
     "hc_launch_count": (C.c_int64, []),
     "hc_bin_pairs_local": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P]),
+    "hc_bin_part_work_bytes": (C.c_int64, [_I64, _I32]),
+    "hc_bin_pairs_local_partitioned": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32,
+                                                 C.POINTER(_I32), _P, _P, _P]),
     "hc_bin_pairs_whole": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _I64, _P, _P]),
     "hc_dense_nonzero_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_dense_nonzero_extract": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
@@ -62,9 +66,9 @@ SIGNATURES = {
     "hc_sort_keys_u64": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, C.POINTER(_I32), _P]),
     "hc_csr_work_bytes": (C.c_int64, [_I64]),
     "hc_csr_count": (C.c_int, [_P, _I64, _P, _P, C.POINTER(_I64), _P]),
-    "hc_csr_emit": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P]),
-    "hc_csr_upper_count": (C.c_int, [_P, _P, _I64, _P, _P]),
-    "hc_csr_upper_emit": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "hc_csr_emit": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "hc_csr_upper_count": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "hc_csr_upper_emit": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P]),
     "hc_ice_csr_marginals": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "hc_ice_csr_work_bytes": (C.c_int64, [_I64, _I32]),
     "hc_ice_csr_balance": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, C.POINTER(_I64), C.POINTER(IceParams),

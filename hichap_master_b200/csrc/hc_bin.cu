@@ -6,6 +6,7 @@
 //
 // Roofline: HBM-bound streaming read of the columnar pairs (16 B/pair, +1 B mark) with 128-bit
 // loads; the += 1 updates are 32-bit RED atomics resolved in L2 (not HBM traffic).
+#include <algorithm>
 #include "hc_common.cuh"
 
 namespace {
@@ -151,6 +152,162 @@ row_nonzero_extract_kernel(const T* __restrict__ M, int64_t ld, int nrows, int n
     }
 }
 
+// ---- partitioned binning: radix partition by chromosome -> L2-resident accumulation --------
+// The direct kernel above is bound by DRAM read-modify-write traffic: random += 1 over 1.2 GB of
+// tiles misses L2 on almost every update (ncu: 31 GB of DRAM traffic for 6.4 GB of pairs).
+// Here the pairs are first partitioned by chromosome into packed (min_bin << 16 | max_bin) keys
+// (one streaming pass: 16 B read + 4 B written per pair); the keys are then accumulated into the
+// UPPER triangles bucket after bucket by persistent CTAs walking the key array in order, so the
+// tile being updated stays in L2; a final tile-transpose pass mirrors upper -> lower.
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 8;                      // pairs per thread per tile
+constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
+constexpr int PART_MAX_BUCKETS = 256;
+
+struct PartArgs {
+    PairCols in; long long npairs; uint32_t res; int mode; int nchrom;
+    const int32_t* mat_n;
+    unsigned long long* bucket_count;   // [nchrom]   accepted pairs per chromosome
+    unsigned long long* bucket_start;   // [nchrom+1] exclusive scan
+    unsigned long long* cursor;         // [nchrom]   running fill of each bucket
+    uint32_t* keys;                     // [accepted] packed keys grouped by chromosome
+    unsigned long long* oob;
+};
+
+// -1: dropped (filtered chromosome / trans / mark); -2: out of range; else chromosome + key
+__device__ __forceinline__ int classify_pair(const PartArgs& a, long long i, uint32_t* key) {
+    const int c1 = a.in.c1[i], c2 = a.in.c2[i];
+    if (c1 < 0 || c1 != c2 || c1 >= a.nchrom) return -1;
+    const int mk = a.in.mark ? a.in.mark[i] : 0;
+    if (!mode_accepts(a.mode, mk)) return -1;
+    const int p1 = a.in.p1[i], p2 = a.in.p2[i];
+    if (p1 < 0 || p2 < 0) return -2;
+    const uint32_t b1 = (uint32_t)p1 / a.res, b2 = (uint32_t)p2 / a.res, n = (uint32_t)a.mat_n[c1];
+    if (b1 >= n || b2 >= n) return -2;
+    *key = (min(b1, b2) << 16) | max(b1, b2);
+    return c1;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(PART_THREADS) bin_partition_kernel(PartArgs a) {
+    __shared__ unsigned int s_cnt[PART_MAX_BUCKETS];
+    __shared__ unsigned long long s_base[PART_MAX_BUCKETS];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long ntiles = (a.npairs + PART_TILE - 1) / PART_TILE;
+    unsigned long long my_oob = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < a.nchrom; i += PART_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        uint32_t key[PART_ITEMS];
+        int bucket[PART_ITEMS];
+        unsigned rank[PART_ITEMS];
+#pragma unroll
+        for (int it = 0; it < PART_ITEMS; ++it) {
+            const long long i = tile * PART_TILE + it * PART_THREADS + threadIdx.x;   // coalesced
+            key[it] = 0;
+            bucket[it] = i < a.npairs ? classify_pair(a, i, &key[it]) : -1;
+            if (bucket[it] == -2) ++my_oob;
+            // warp-aggregated rank: one shared-memory atomic per distinct chromosome per warp
+            const int bk = bucket[it] >= 0 ? bucket[it] : PART_MAX_BUCKETS + lane;
+            const unsigned m = __match_any_sync(0xffffffffu, bk);
+            unsigned base = 0;
+            const int leader = __ffs(m) - 1;
+            if (bucket[it] >= 0 && lane == leader) base = atomicAdd(&s_cnt[bucket[it]], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            rank[it] = base + __popc(m & lt);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < a.nchrom; c += PART_THREADS) {
+            const unsigned n = s_cnt[c];
+            if (!SCATTER) { if (n) atomicAdd(&a.bucket_count[c], (unsigned long long)n); }
+            else s_base[c] = a.bucket_start[c] + (n ? atomicAdd(&a.cursor[c], (unsigned long long)n) : 0ull);
+        }
+        if (SCATTER) {
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < PART_ITEMS; ++it)
+                if (bucket[it] >= 0) a.keys[s_base[bucket[it]] + rank[it]] = key[it];
+        }
+        __syncthreads();
+    }
+    if (!SCATTER && a.oob) {
+        my_oob = (unsigned long long)warp_sum_ll((long long)my_oob);
+        if (lane == 0 && my_oob) atomicAdd(a.oob, my_oob);
+    }
+}
+
+__global__ void bin_partition_scan_kernel(PartArgs a) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int c = 0; c < a.nchrom; ++c) { a.bucket_start[c] = run; run += a.bucket_count[c]; a.cursor[c] = 0; }
+        a.bucket_start[a.nchrom] = run;
+    }
+}
+
+// persistent CTAs walk the grouped keys front to back: concurrently running CTAs update the same
+// one or two chromosomes, whose upper triangles fit L2
+__global__ void __launch_bounds__(256)
+bin_accumulate_kernel(const uint32_t* __restrict__ keys, const unsigned long long* __restrict__ bucket_start, int nchrom,
+                      int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off, const int32_t* __restrict__ mat_ld) {
+    const long long total = (long long)bucket_start[nchrom];
+    constexpr int CHUNK = 256 * 8;
+    for (long long base = (long long)blockIdx.x * CHUNK; base < total; base += (long long)gridDim.x * CHUNK) {
+        int c = 0;                                   // bucket of the chunk's first key (binary search)
+        {
+            int lo = 0, hi = nchrom - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)bucket_start[mid] <= base) lo = mid; else hi = mid - 1; }
+            c = lo;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const long long i = base + it * 256 + threadIdx.x;
+            if (i < total) {
+                int cc = c;
+                while ((long long)bucket_start[cc + 1] <= i) ++cc;
+                const uint32_t k = keys[i];
+                atomicAdd(&mats[mat_off[cc] + (int64_t)(k >> 16) * mat_ld[cc] + (k & 0xffffu)], 1);
+            }
+        }
+    }
+}
+
+// lower = transpose(upper) for every matrix of the batch (32x32 tiles through shared memory)
+struct MirrorTab { int nprob; int start[PART_MAX_BUCKETS + 1]; };   // prefix of T_p(T_p+1)/2 tile pairs per matrix
+
+__global__ void __launch_bounds__(256)
+mirror_upper_kernel(int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off, const int32_t* __restrict__ mat_n,
+                    const int32_t* __restrict__ mat_ld, MirrorTab tab) {
+    __shared__ int32_t t[32][33];
+    int p = 0;
+    {
+        int lo = 0, hi = tab.nprob - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab.start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+        p = lo;
+    }
+    const int n = mat_n[p];
+    // destination tile (row block I, col block J), I >= J, enumerated row by row
+    const int idx = blockIdx.x - tab.start[p];
+    int I = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > idx) --I;
+    while ((I + 1) * (I + 2) / 2 <= idx) ++I;
+    const int J = idx - I * (I + 1) / 2;
+    int32_t* M = mats + mat_off[p];
+    const int64_t ld = mat_ld[p];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {               // source tile (J, I): rows J*32.., cols I*32..
+        const int sr = J * 32 + r, sc = I * 32 + tx;
+        t[r][tx] = (sr < n && sc < n) ? M[(int64_t)sr * ld + sc] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int dr = I * 32 + r, dc = J * 32 + tx;
+        if (dr < n && dc < n && dr > dc) M[(int64_t)dr * ld + dc] = t[tx][r];
+    }
+}
+
 // ---- whole batch at once: upper-triangular records in the reference's 24-byte layout ------
 struct Rec24 { long long bin1; long long bin2; double IF; };   // matrixBuilding.py:460-461 S_dtype
 
@@ -248,6 +405,57 @@ extern "C" int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const in
     bin_pairs_kernel<false><<<bin_grid(npairs), BIN_THREADS, 0, (cudaStream_t)stream>>>(
         in, npairs, (uint32_t)res, mode, mats, mat_off, nullptr, mat_n, mat_ld, nchrom, 0, 0, oob);
     HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+// Partitioned variant of hc_bin_pairs_local for SYMMETRIC modes on matrices that are symmetric on
+// entry (e.g. freshly zeroed): same result, ~3x less DRAM traffic.  work: hc_bin_part_work_bytes.
+extern "C" int64_t hc_bin_part_work_bytes(int64_t npairs, int32_t nchrom) {
+    return (int64_t)sizeof(uint32_t) * (npairs > 0 ? npairs : 1) + (int64_t)sizeof(unsigned long long) * (3 * (int64_t)nchrom + 2) + 64;
+}
+
+extern "C" int hc_bin_pairs_local_partitioned(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                                              const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                                              int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                              const int32_t* mat_ld, int32_t nchrom, const int32_t* h_mat_n,
+                                              unsigned long long* oob, void* work, void* stream) {
+    HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0, "npairs>=0, res>0, nchrom>0");
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mode == HC_BIN_SYM_BOTH, "partitioned binning is for the symmetric modes");
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
+    HC_REQUIRE(nchrom <= PART_MAX_BUCKETS && h_mat_n != nullptr, "at most 256 chromosomes; h_mat_n");
+    MirrorTab mtab;
+    mtab.nprob = nchrom;
+    mtab.start[0] = 0;
+    for (int p = 0; p < nchrom; ++p) {
+        HC_REQUIRE(h_mat_n[p] >= 0 && h_mat_n[p] <= 65536, "matrix side must be <= 65536 bins");
+        const long long T = (h_mat_n[p] + 31) / 32;
+        const long long nxt = mtab.start[p] + T * (T + 1) / 2;
+        HC_REQUIRE(nxt < (1ll << 31), "too many tiles");
+        mtab.start[p + 1] = (int)nxt;
+    }
+    if (npairs == 0) return HC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    PartArgs a;
+    a.in = PairCols{c1, p1, c2, p2, mark}; a.npairs = npairs; a.res = (uint32_t)res; a.mode = mode; a.nchrom = nchrom;
+    a.mat_n = mat_n; a.oob = oob;
+    unsigned long long* tab = reinterpret_cast<unsigned long long*>(work);
+    a.bucket_count = tab; a.bucket_start = tab + nchrom; a.cursor = tab + 2 * nchrom + 1;
+    a.keys = reinterpret_cast<uint32_t*>(tab + 3 * nchrom + 2);
+    HC_CUDA(cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * (3 * (size_t)nchrom + 2), s));
+    const long long ntiles = (npairs + PART_TILE - 1) / PART_TILE;
+    const int grid = (int)std::min<long long>(ntiles, (long long)hc_num_sms() * 8);
+    bin_partition_kernel<false><<<grid, PART_THREADS, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    bin_partition_scan_kernel<<<1, 32, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    bin_partition_kernel<true><<<grid, PART_THREADS, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    bin_accumulate_kernel<<<hc_num_sms() * 8, 256, 0, s>>>(a.keys, a.bucket_start, nchrom, mats, mat_off, mat_ld);
+    HC_LAUNCH_CHECK();
+    if (mtab.start[nchrom] > 0) {
+        mirror_upper_kernel<<<mtab.start[nchrom], 256, 0, s>>>(mats, mat_off, mat_n, mat_ld, mtab);
+        HC_LAUNCH_CHECK();
+    }
     return HC_OK;
 }
 

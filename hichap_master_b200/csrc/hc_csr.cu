@@ -130,7 +130,7 @@ rle_emit_kernel(const unsigned long long* __restrict__ keys, const unsigned long
 // (col, count) per unique key and the row pointer
 __global__ void __launch_bounds__(256)
 csr_finish_kernel(const unsigned long long* __restrict__ ukey, const int64_t* __restrict__ upos, long long nnz,
-                  const unsigned long long* __restrict__ n_valid_p, int col_bits, long long nrows,
+                  const unsigned long long* __restrict__ n_valid_p, int col_bits, long long row0, long long nrows,
                   int64_t* __restrict__ row_ptr, int32_t* __restrict__ col, int32_t* __restrict__ cnt) {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= nnz) {
@@ -138,31 +138,32 @@ csr_finish_kernel(const unsigned long long* __restrict__ ukey, const int64_t* __
         return;
     }
     const unsigned long long k = ukey[u];
-    const long long row = (long long)(k >> col_bits);
+    const long long row = (long long)(k >> col_bits) - row0;
     col[u] = (int32_t)(k & ((1ull << col_bits) - 1ull));
     const long long next = (u + 1 < nnz) ? upos[u + 1] : (long long)*n_valid_p;
     cnt[u] = (int32_t)(next - upos[u]);
-    const long long prev_row = u == 0 ? -1 : (long long)(ukey[u - 1] >> col_bits);
+    const long long prev_row = u == 0 ? -1 : (long long)(ukey[u - 1] >> col_bits) - row0;
     for (long long r = prev_row + 1; r <= row; ++r) row_ptr[r] = u;     // rows (prev_row, row] start here
     if (u == nnz - 1) for (long long r = row + 1; r <= nrows; ++r) row_ptr[r] = nnz;
 }
 
 // upper-triangular records of the symmetric CSR (col >= row), row-major: count then emit
 __global__ void __launch_bounds__(256)
-csr_upper_count_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, long long nrows,
-                       int64_t* __restrict__ out_cnt) {
+csr_upper_count_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, long long row0,
+                       long long nrows, int64_t* __restrict__ out_cnt) {
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= nrows) return;
     int c = 0;
-    for (long long e = row_ptr[r] + lane; e < row_ptr[r + 1]; e += 32) c += col[e] >= r;
+    for (long long e = row_ptr[r] + lane; e < row_ptr[r + 1]; e += 32) c += col[e] >= r + row0;
     c = warp_sum_i(c);
     if (lane == 0) out_cnt[r] = c;
 }
 
 __global__ void __launch_bounds__(256)
 csr_upper_emit_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                      const int32_t* __restrict__ cnt, long long nrows, const int64_t* __restrict__ out_ptr,
+                      const int32_t* __restrict__ cnt, long long row0, long long nrows,
+                      const int64_t* __restrict__ out_ptr,
                       int32_t* __restrict__ bin1, int32_t* __restrict__ bin2, int32_t* __restrict__ val) {
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -171,11 +172,11 @@ csr_upper_emit_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __rest
     const long long e1 = row_ptr[r + 1];
     for (long long e0 = row_ptr[r]; e0 < e1; e0 += 32) {
         const long long e = e0 + lane;
-        const bool keep = e < e1 && col[e] >= r;
+        const bool keep = e < e1 && col[e] >= r + row0;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const long long o = out + __popc(b & ((1u << lane) - 1u));
-            bin1[o] = (int32_t)r; bin2[o] = col[e]; val[o] = cnt[e];
+            bin1[o] = (int32_t)(r + row0); bin2[o] = col[e]; val[o] = cnt[e];
         }
         out += __popc(b);
     }
@@ -223,10 +224,11 @@ extern "C" int hc_csr_count(const unsigned long long* sorted_keys, int64_t nkeys
     return HC_OK;
 }
 
-// Emit the CSR.  ukey/upos: nnz-element scratch (the free ping-pong buffer of the sort is
+// Emit the CSR of rows [row0, row0+nrows) (every key's row must lie in that range; row_ptr is
+// indexed by LOCAL row).  ukey/upos: nnz-element scratch (the free ping-pong buffer of the sort is
 // large enough for both).  row_ptr: nrows+1; col, cnt: nnz.
 extern "C" int hc_csr_emit(const unsigned long long* sorted_keys, int64_t nkeys, const unsigned long long* n_valid,
-                           const void* work, int64_t nnz, int32_t col_bits, int64_t nrows,
+                           const void* work, int64_t nnz, int32_t col_bits, int64_t row0, int64_t nrows,
                            unsigned long long* ukey, int64_t* upos, int64_t* row_ptr, int32_t* col, int32_t* cnt,
                            void* stream) {
     HC_REQUIRE(nkeys >= 0 && nnz >= 0 && nrows >= 0, "sizes");
@@ -238,20 +240,21 @@ extern "C" int hc_csr_emit(const unsigned long long* sorted_keys, int64_t nkeys,
         HC_LAUNCH_CHECK();
     }
     const long long blocks = (nnz + 1 + 255) / 256;
-    csr_finish_kernel<<<(unsigned)blocks, 256, 0, s>>>(ukey, upos, nnz, n_valid, col_bits, nrows, row_ptr, col, cnt);
+    csr_finish_kernel<<<(unsigned)blocks, 256, 0, s>>>(ukey, upos, nnz, n_valid, col_bits, row0, nrows, row_ptr, col, cnt);
     HC_LAUNCH_CHECK();
     return HC_OK;
 }
 
-// Upper-triangular (bin1, bin2, count) records of a symmetric CSR, rows [0,nrows), row-major.
+// Upper-triangular (bin1, bin2, count) records (global bins) of the local rows [row0, row0+nrows)
+// of a symmetric CSR, row-major.
 // Two calls like hc_dense_nonzero_*: count fills out_ptr[nrows+1] (exclusive scan), then emit.
-extern "C" int hc_csr_upper_count(const int64_t* row_ptr, const int32_t* col, int64_t nrows, int64_t* out_ptr,
-                                  void* stream) {
+extern "C" int hc_csr_upper_count(const int64_t* row_ptr, const int32_t* col, int64_t row0, int64_t nrows,
+                                  int64_t* out_ptr, void* stream) {
     HC_REQUIRE(nrows >= 0, "nrows");
     cudaStream_t s = (cudaStream_t)stream;
     if (nrows > 0) {
         const long long blocks = (nrows * 32 + 255) / 256;
-        csr_upper_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(row_ptr, col, nrows, out_ptr);
+        csr_upper_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(row_ptr, col, row0, nrows, out_ptr);
         HC_LAUNCH_CHECK();
     }
     csr_exclusive_scan_kernel<<<1, 1024, 0, s>>>(out_ptr, nrows);
@@ -259,12 +262,12 @@ extern "C" int hc_csr_upper_count(const int64_t* row_ptr, const int32_t* col, in
     return HC_OK;
 }
 
-extern "C" int hc_csr_upper_emit(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t nrows,
-                                 const int64_t* out_ptr, int32_t* bin1, int32_t* bin2, int32_t* val, void* stream) {
+extern "C" int hc_csr_upper_emit(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t row0,
+                                 int64_t nrows, const int64_t* out_ptr, int32_t* bin1, int32_t* bin2, int32_t* val, void* stream) {
     HC_REQUIRE(nrows >= 0, "nrows");
     if (nrows == 0) return HC_OK;
     const long long blocks = (nrows * 32 + 255) / 256;
-    csr_upper_emit_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(row_ptr, col, cnt, nrows, out_ptr,
+    csr_upper_emit_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(row_ptr, col, cnt, row0, nrows, out_ptr,
                                                                              bin1, bin2, val);
     HC_LAUNCH_CHECK();
     return HC_OK;

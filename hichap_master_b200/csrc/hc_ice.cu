@@ -125,13 +125,12 @@ ice_filter_mad_kernel(const double* __restrict__ marg, int64_t nbins, double mad
 struct IceDenseArgs {
     const int32_t* mats; const int64_t* mat_off; const int32_t* mat_n; const int32_t* mat_ld;
     const int64_t* pad_off;     // start of each problem in the padded (ld-strided, 128 B aligned) vectors
-    const int32_t* cta_prob; const int32_t* cta_row0; const int32_t* cta_row1;
-    const int32_t* prob_ncta;   // CTAs working on each problem
-    int32_t* ticket;            // per problem: CTAs finished in this launch (reset by the last one)
-    double* bias;               // padded layout; updated in place by the tail of each problem
-    double* marg;               // padded layout; fresh marginals of this launch
+    const int32_t* item_prob; const int32_t* item_row0; const int32_t* item_nrows;   // work items (~equal bytes)
+    unsigned int nitems; unsigned int* queue;   // global work queue: warps draw items until it runs dry
+    double* bias;               // padded layout; updated in place by the update kernel
+    double* marg;               // padded layout; fresh marginals of this iteration
     hc_ice_result* results; int32_t* done; int32_t* n_done;
-    double tol; int kd; int max_iters;
+    double tol; int kd; int max_iters; int nprob;
 };
 
 // one column chunk (128 columns, 4 per lane) of RG rows: acc[q] += sum_j w * A[rq][j] * b[j]
@@ -154,80 +153,90 @@ __device__ __forceinline__ void consume_chunk(const int4 (&a)[RG], const double*
     }
 }
 
+// Streaming half of an iteration: marg[r] = b[r] * sum_j w(r,j) A[r][j] b[j] for every row of every
+// unconverged chromosome.  Persistent warps draw row-group items (~48 KB each) from a global queue,
+// so the launch stays balanced however the chromosomes differ in size; the next item is drawn
+// before the current one is processed, hiding the atomic's latency behind the row loads.
 template <int RG, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-ice_dense_iter_kernel(IceDenseArgs A, int k) {
+ice_dense_stream_kernel(IceDenseArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(A.queue, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < A.nitems) {
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(A.queue, 1u);
+        const int p = A.item_prob[item];
+        if (!A.done[p]) {
+            const int ld = A.mat_ld[p];            // multiple of 128: every 128-column chunk is full
+            const int nchunk = ld >> 7;
+            const int64_t lo = A.pad_off[p];
+            const int32_t* mat = A.mats + A.mat_off[p];
+            const double* __restrict__ b = A.bias + lo;
+            double* mout = A.marg + lo;
+            const int r0 = A.item_row0[item], r1 = r0 + A.item_nrows[item];
+            for (int rg = r0; rg < r1; rg += RG) {
+                const int nr = min(RG, r1 - rg);
+                const int32_t* base = mat + (int64_t)rg * ld + 4 * lane;
+                int roff[RG];                      // ragged last group: re-read the last valid row, discard below
+#pragma unroll
+                for (int q = 0; q < RG; ++q) roff[q] = min(q, nr - 1) * ld;
+                double acc[RG];
+#pragma unroll
+                for (int q = 0; q < RG; ++q) acc[q] = 0.0;
+                int c0 = 0;
+                for (; c0 + U <= nchunk; c0 += U) {   // RG x U independent 128-bit streaming loads in flight per lane
+                    int4 a[U][RG];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int q = 0; q < RG; ++q) a[u][q] = ld_stream_v4(base + roff[q] + (c0 + u) * 128);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        consume_chunk<RG>(a[u], b, (c0 + u) * 128 + 4 * lane, (c0 + u) * 128, rg, kd, kspan, acc);
+                }
+                for (; c0 < nchunk; ++c0) {
+                    int4 a[RG];
+#pragma unroll
+                    for (int q = 0; q < RG; ++q) a[q] = ld_stream_v4(base + roff[q] + c0 * 128);
+                    consume_chunk<RG>(a, b, c0 * 128 + 4 * lane, c0 * 128, rg, kd, kspan, acc);
+                }
+#pragma unroll
+                for (int q = 0; q < RG; ++q) {
+                    const double sacc = warp_sum(acc[q]);
+                    if (lane == 0 && q < nr) mout[rg + q] = b[rg + q] * sacc;
+                }
+            }
+        }
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// Vector half of an iteration (grid = one CTA per chromosome): mean / variance of the fresh
+// marginals over the non-zero bins, bias update b /= marg/mean (in place), convergence test,
+// scale / iteration bookkeeping -- all on the device.
+__global__ void __launch_bounds__(256)
+ice_dense_update_kernel(IceDenseArgs A, int k) {
     __shared__ double red[32];
     __shared__ long long redll[32];
-    __shared__ int flag_s;
-
-    const int p = A.cta_prob[blockIdx.x];
-    if (A.done[p]) return;                 // set by the tail of an EARLIER launch: uniform for the CTA
+    const int p = blockIdx.x;
+    if (p == 0 && threadIdx.x == 0) *A.queue = 0;         // re-arm the work queue for the next iteration
+    if (A.done[p]) return;
     const int n = A.mat_n[p];
-    const int ld = A.mat_ld[p];            // multiple of 128: every 128-column chunk is full
+    if (n == 0) return;
     const int64_t lo = A.pad_off[p];
-    const int row0 = A.cta_row0[blockIdx.x], row1 = A.cta_row1[blockIdx.x];
-
-    // ---- body: marg[r] = b[r] * sum_j w(r,j) A[r][j] b[j] -------------------------------------
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nchunk = ld >> 7;
-    const int32_t* mat = A.mats + A.mat_off[p];
-    const double* __restrict__ b = A.bias + lo;
-    double* mout = A.marg + lo;
-    const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
-    for (int rg = row0 + wid * RG; rg < row1; rg += nw * RG) {
-        const int nr = min(RG, row1 - rg);
-        const int32_t* base = mat + (int64_t)rg * ld + 4 * lane;
-        int roff[RG];                      // ragged last group: re-read the last valid row, discard below
-#pragma unroll
-        for (int q = 0; q < RG; ++q) roff[q] = min(q, nr - 1) * ld;
-        double acc[RG];
-#pragma unroll
-        for (int q = 0; q < RG; ++q) acc[q] = 0.0;
-        int c0 = 0;
-        for (; c0 + U <= nchunk; c0 += U) {   // RG x U independent 128-bit streaming loads in flight per lane
-            int4 a[U][RG];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int q = 0; q < RG; ++q) a[u][q] = ld_stream_v4(base + roff[q] + (c0 + u) * 128);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                consume_chunk<RG>(a[u], b, (c0 + u) * 128 + 4 * lane, (c0 + u) * 128, rg, kd, kspan, acc);
-        }
-        for (; c0 < nchunk; ++c0) {
-            int4 a[RG];
-#pragma unroll
-            for (int q = 0; q < RG; ++q) a[q] = ld_stream_v4(base + roff[q] + c0 * 128);
-            consume_chunk<RG>(a, b, c0 * 128 + 4 * lane, c0 * 128, rg, kd, kspan, acc);
-        }
-#pragma unroll
-        for (int q = 0; q < RG; ++q) {
-            const double sacc = warp_sum(acc[q]);
-            if (lane == 0 && q < nr) mout[rg + q] = b[rg + q] * sacc;
-        }
-    }
-
-    // ---- tail: the last CTA of this problem reduces, updates the bias and tests convergence --
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();                                   // publish this CTA's marginals
-        const int t = atomicAdd(A.ticket + p, 1);
-        flag_s = (t == A.prob_ncta[p] - 1);
-    }
-    __syncthreads();
-    if (!flag_s) return;
-    __threadfence();                                       // acquire the other CTAs' marginals
-    if (threadIdx.x == 0) A.ticket[p] = 0;                 // ready for the next launch
+    const double* m_in = A.marg + lo;
+    double* bw = A.bias + lo;
     double s = 0.0;
     long long c = 0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double m = __ldcg(mout + j);                 // written by other SMs: bypass L1
+        const double m = m_in[j];
         if (m != 0.0) { s += m; ++c; }
     }
     s = block_sum(s, red);
     c = block_sum_ll(c, redll);
-    double* bw = A.bias + lo;
     if (c == 0) {   // nothing left to balance: cooler sets bias = NaN, scale = NaN, var = 0
         if (threadIdx.x == 0) {
             hc_ice_result r; r.scale = __longlong_as_double(0x7ff8000000000000ll); r.var = 0.0;
@@ -239,12 +248,12 @@ ice_dense_iter_kernel(IceDenseArgs A, int k) {
     const double mean = s / (double)c;
     double v = 0.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double m = __ldcg(mout + j);
+        const double m = m_in[j];
         if (m != 0.0) { const double d = m - mean; v += d * d; }
     }
     const double var = block_sum(v, red) / (double)c;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double m = __ldcg(mout + j) / mean;
+        double m = m_in[j] / mean;
         if (m == 0.0) m = 1.0;
         bw[j] = bw[j] / m;
     }
@@ -286,16 +295,16 @@ ice_finalize_kernel(const int64_t* __restrict__ bin_off, const int64_t* __restri
     bias[g] = b;
 }
 
-typedef void (*IterKernel)(IceDenseArgs, int);
-struct IterVariant { IterKernel fn; int rg, u, minb; };
-// tuned on B200 (profiles/): more rows per warp = fewer bias reads; RG*U 128-bit loads in flight per lane
-const IterVariant kVariants[] = {
-    {ice_dense_iter_kernel<2, 2, 4>, 2, 2, 4},   // default: 5.28 TB/s on C2 (profiles/r1b_ice_variants.log)
-    {ice_dense_iter_kernel<4, 2, 3>, 4, 2, 3},
-    {ice_dense_iter_kernel<2, 4, 3>, 2, 4, 3},
-    {ice_dense_iter_kernel<4, 2, 4>, 4, 2, 4},
-    {ice_dense_iter_kernel<4, 4, 2>, 4, 4, 2},
-    {ice_dense_iter_kernel<8, 2, 2>, 8, 2, 2},
+typedef void (*StreamKernel)(IceDenseArgs);
+struct StreamVariant { StreamKernel fn; int rg, u, minb; };
+// tuned on B200 (profiles/): RG rows share the bias loads; RG*U 128-bit loads in flight per lane
+const StreamVariant kVariants[] = {
+    {ice_dense_stream_kernel<4, 2, 4>, 4, 2, 4},   // default: 5.5 TB/s on C2 (profiles/r1c_ice_variants_v3.log)
+    {ice_dense_stream_kernel<4, 2, 3>, 4, 2, 3},
+    {ice_dense_stream_kernel<2, 2, 4>, 2, 2, 4},
+    {ice_dense_stream_kernel<2, 4, 3>, 2, 4, 3},
+    {ice_dense_stream_kernel<4, 4, 2>, 4, 4, 2},
+    {ice_dense_stream_kernel<1, 4, 4>, 1, 4, 4},
 };
 
 }  // namespace
@@ -338,11 +347,9 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     HC_REQUIRE(P->max_iters >= 1 && P->ignore_diags >= 0, "max_iters>=1, ignore_diags>=0");
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nbins = 0;
-    double sum_sq = 0.0;
     for (int p = 0; p < nprob; ++p) {
         HC_REQUIRE(h_mat_n[p] >= 0, "matrix side");
         nbins += h_mat_n[p];
-        sum_sq += (double)h_mat_n[p] * (double)h_mat_n[p];
     }
     if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; }
     if (nbins == 0) return HC_OK;
@@ -350,28 +357,9 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     int vi = 0;
     if (const char* e = getenv("HC_ICE_VARIANT")) vi = atoi(e);
     if (vi < 0 || vi >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) vi = 0;
-    const IterVariant V = kVariants[vi];
-    int waves = 2;   // CTAs per resident slot: finer row ranges balance the tail of each launch
-    if (const char* e = getenv("HC_ICE_WAVES")) waves = std::max(1, atoi(e));
-
-    // ---- static work plan: CTAs per problem proportional to n^2; contiguous row ranges whose
-    //      length is a multiple of (8 warps x RG rows) so every warp of a CTA gets whole row groups
-    const int G = hc_num_sms() * V.minb * waves;
-    const int unit = 8 * V.rg;
-    std::vector<int32_t> cta_prob, cta_row0, cta_row1, prob_ncta(nprob, 0);
-    for (int p = 0; p < nprob; ++p) {
-        const int n = h_mat_n[p];
-        if (n == 0) continue;
-        int nc = (int)llround((double)G * ((double)n * n) / sum_sq);
-        const int units = (n + unit - 1) / unit;
-        nc = std::max(1, std::min(nc, units));
-        const int per = (units + nc - 1) / nc * unit;          // rows per CTA
-        for (int r0 = 0; r0 < n; r0 += per) {
-            cta_prob.push_back(p); cta_row0.push_back(r0); cta_row1.push_back(std::min(n, r0 + per));
-            ++prob_ncta[p];
-        }
-    }
-    const int ncta = (int)cta_prob.size();
+    const StreamVariant V = kVariants[vi];
+    int item_kb = 32;   // bytes of matrix per work item: small enough that the last item is a short tail
+    if (const char* e = getenv("HC_ICE_ITEM_KB")) item_kb = std::max(1, atoi(e));
 
     // padded internal vectors: problem p owns [pad_off[p], pad_off[p] + ld_p), 128-byte aligned, so the
     // kernel can read the bias of any 4-column group with two aligned 16-byte loads and never
@@ -390,6 +378,28 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     }
     const int64_t npad = h_pad[nprob];
     (void)work;   // scratch is allocated stream-ordered below; `work` is kept for ABI stability
+
+    // ---- work items: RG-aligned row groups of ~item_kb KB, largest chromosomes first -----------
+    std::vector<int32_t> h_done(nprob, 0);
+    std::vector<int32_t> item_prob, item_row0, item_nrows;
+    auto build_items = [&]() {
+        item_prob.clear(); item_row0.clear(); item_nrows.clear();
+        std::vector<int> order(nprob);
+        for (int p = 0; p < nprob; ++p) order[p] = p;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h_mat_n[a] > h_mat_n[b]; });
+        for (int p : order) {
+            const int n = h_mat_n[p];
+            if (n == 0 || h_done[p]) continue;
+            int rows = (int)((int64_t)item_kb * 1024 / ((int64_t)h_ld[p] * 4));
+            rows = std::max(V.rg, rows / V.rg * V.rg);
+            for (int r0 = 0; r0 < n; r0 += rows) {
+                item_prob.push_back(p); item_row0.push_back(r0); item_nrows.push_back(std::min(rows, n - r0));
+            }
+        }
+    };
+    build_items();
+    const size_t max_items = item_prob.size();
+
     double* d_vec = nullptr;     // [npad] bias | [npad] marg | [nprob+1] pad_off (as int64)
     HC_CUDA(cudaMallocAsync((void**)&d_vec, (2 * (size_t)npad + nprob + 1) * sizeof(double), s));
     double* biasp = d_vec;
@@ -399,28 +409,33 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     HC_CUDA(cudaMemcpyAsync(d_pad, h_pad.data(), (nprob + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ice_pad_bias_kernel<<<(unsigned)((nbins + 255) / 256), 256, 0, s>>>(bin_off, d_pad, nprob, bias, biasp);
     HC_LAUNCH_CHECK();
-    int32_t* d_tab = nullptr;
-    const size_t tab_ints = (size_t)3 * ncta + 3 * (size_t)nprob + 1;
+    int32_t* d_tab = nullptr;    // 3 item tables | done[nprob] | n_done | queue
+    const size_t tab_ints = 3 * max_items + (size_t)nprob + 2;
     HC_CUDA(cudaMallocAsync((void**)&d_tab, tab_ints * sizeof(int32_t), s));
-    HC_CUDA(cudaMemcpyAsync(d_tab, cta_prob.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HC_CUDA(cudaMemcpyAsync(d_tab + ncta, cta_row0.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HC_CUDA(cudaMemcpyAsync(d_tab + 2 * ncta, cta_row1.data(), ncta * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HC_CUDA(cudaMemcpyAsync(d_tab + 3 * ncta, prob_ncta.data(), nprob * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    HC_CUDA(cudaMemsetAsync(d_tab + 3 * ncta + nprob, 0, (2 * (size_t)nprob + 1) * sizeof(int32_t), s));
+    auto upload_items = [&]() -> cudaError_t {
+        const size_t n = item_prob.size();
+        cudaError_t e = cudaMemcpyAsync(d_tab, item_prob.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab + max_items, item_row0.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab + 2 * max_items, item_nrows.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the host vectors may be rebuilt afterwards
+        return e;
+    };
+    HC_CUDA(upload_items());
+    HC_CUDA(cudaMemsetAsync(d_tab + 3 * max_items, 0, ((size_t)nprob + 2) * sizeof(int32_t), s));
 
     IceDenseArgs A;
     A.mats = mats; A.mat_off = mat_off; A.mat_n = mat_n; A.mat_ld = mat_ld; A.pad_off = d_pad;
-    A.cta_prob = d_tab; A.cta_row0 = d_tab + ncta; A.cta_row1 = d_tab + 2 * ncta;
-    A.prob_ncta = d_tab + 3 * ncta;
-    A.ticket = d_tab + 3 * ncta + nprob;
-    A.done = d_tab + 3 * ncta + 2 * nprob;
-    A.n_done = d_tab + 3 * ncta + 3 * nprob;
+    A.item_prob = d_tab; A.item_row0 = d_tab + max_items; A.item_nrows = d_tab + 2 * max_items;
+    A.nitems = (unsigned)item_prob.size();
+    A.done = d_tab + 3 * max_items;
+    A.n_done = A.done + nprob;
+    A.queue = reinterpret_cast<unsigned int*>(A.n_done + 1);
     A.bias = biasp; A.marg = marg; A.results = results;
-    A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters;
+    A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters; A.nprob = nprob;
 
     int nonempty = 0;
     for (int p = 0; p < nprob; ++p) nonempty += h_mat_n[p] > 0;
-    if (nonempty != nprob) {   // empty problems never get a CTA: give them a defined result
+    if (nonempty != nprob) {   // empty problems never get work: give them a defined result
         std::vector<hc_ice_result> h_res(nprob);
         for (int p = 0; p < nprob; ++p) { h_res[p].scale = NAN; h_res[p].var = 0.0; h_res[p].iters = 0; h_res[p].converged = 1; }
         HC_CUDA(cudaMemcpyAsync(results, h_res.data(), sizeof(hc_ice_result) * nprob, cudaMemcpyHostToDevice, s));
@@ -428,21 +443,30 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     }
     // the bias vector is the only data that should live in L1: no shared-memory carve-out
     cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    const int grid = hc_num_sms() * V.minb;    // persistent: every resident slot filled exactly once
 
     const int poll = P->poll_every > 0 ? P->poll_every : 8;
-    int launches = 0, h_done = 0;
+    int launches = 0, h_ndone = 0, seen_done = 0;
     int rc = HC_OK;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the iteration loop, for the roofline
     if (h_info) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, s); }
     for (int k = 1; k <= P->max_iters; ++k) {
-        V.fn<<<ncta, 256, 0, s>>>(A, k);
-        hc_count_launch();
-        ++launches;
+        V.fn<<<grid, 256, 0, s>>>(A);
+        ice_dense_update_kernel<<<nprob, 256, 0, s>>>(A, k);
+        hc_count_launch(2);
+        launches += 2;
         if (k % poll == 0 || k == P->max_iters) {
-            cudaError_t e = cudaMemcpyAsync(&h_done, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+            cudaError_t e = cudaMemcpyAsync(&h_ndone, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess && h_ndone >= nonempty) break;
+            if (e == cudaSuccess && h_ndone != seen_done) {
+                // drop the converged chromosomes from the work list (their items would only be skipped)
+                seen_done = h_ndone;
+                e = cudaMemcpyAsync(h_done.data(), A.done, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (e == cudaSuccess) { build_items(); e = upload_items(); A.nitems = (unsigned)item_prob.size(); }
+            }
             if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
-            if (h_done >= nonempty) break;
         }
     }
     if (h_info && ev0) cudaEventRecord(ev1, s);
@@ -456,7 +480,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     }
     cudaFreeAsync(d_tab, s);
     cudaFreeAsync(d_vec, s);
-    cudaError_t e = cudaStreamSynchronize(s);  // host tables above must outlive the copies
+    cudaError_t e = cudaStreamSynchronize(s);
     if (rc == HC_OK && e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; }
     if (h_info) {
         h_info->launches = launches;

@@ -13,10 +13,19 @@ from . import _abi
 ROW_ALIGN = 128  # int32 elements -> 512-byte rows: every 128-column chunk a warp streams is full
 
 
+_inited = set()
+
+
 def require_cuda(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise _abi.HcError("hichap_master_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _inited:
+        with torch.cuda.device(idx):
+            _abi.check(_abi.lib().hc_init(), "hc_init")
+        _inited.add(idx)
+    return dev
 
 
 def stream_ptr() -> C.c_void_p:

@@ -44,6 +44,27 @@ def bin_pairs_local(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.H
         _raise_oob(oob, "intra-chromosomal")
 
 
+def bin_pairs_local_partitioned(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
+                                check_bounds=True, work=None):
+    """``bin_pairs_local`` for the symmetric modes on matrices that are symmetric on entry
+    (freshly zeroed tiles): radix partition by chromosome, L2-resident accumulation of the upper
+    triangles, mirror.  Falls back to the direct kernel outside its limits."""
+    if len(batch) > 256 or max(batch.sizes) > 65536 or mode == _abi.HC_BIN_ONESIDED:
+        return bin_pairs_local(pairs, res, batch, mode, check_bounds)
+    oob = _oob_counter(batch.device)
+    nbytes = int(lib().hc_bin_part_work_bytes(pairs.n, len(batch)))
+    if work is None or work.numel() < nbytes:
+        work = torch.empty(nbytes, dtype=torch.uint8, device=batch.device)
+    check(lib().hc_bin_pairs_local_partitioned(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
+                                               ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(batch.buf),
+                                               ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld), len(batch),
+                                               batch.h_mat_n, ptr(oob), ptr(work), stream_ptr()),
+          "hc_bin_pairs_local_partitioned")
+    if check_bounds:
+        _raise_oob(oob, "intra-chromosomal")
+    return work
+
+
 def bin_pairs_whole(pairs: PairColumns, res: int, start1, start2, whole: DenseBatch,
                     mode=_abi.HC_BIN_SYM_ALL, check_bounds=True):
     """Accumulate pairs into the single genome-wide matrix ``whole`` (a 1-matrix batch) with
@@ -255,7 +276,7 @@ class SymCsr:
         self.device = col.device
 
 
-def keys_to_csr(sorted_keys, n_valid, col_bits: int, nrows: int, scratch=None):
+def keys_to_csr(sorted_keys, n_valid, col_bits: int, nrows: int, scratch=None, row0: int = 0):
     """Reduce-by-key over sorted keys -> (row_ptr int64[nrows+1], col int32, cnt int32)."""
     dev, nkeys = sorted_keys.device, int(sorted_keys.numel())
     work = torch.empty(int(lib().hc_csr_work_bytes(nkeys)), dtype=torch.uint8, device=dev)
@@ -268,9 +289,32 @@ def keys_to_csr(sorted_keys, n_valid, col_bits: int, nrows: int, scratch=None):
     cnt = torch.empty(nnz, dtype=torch.int32, device=dev)
     ukey = scratch if (scratch is not None and scratch.numel() >= nnz) else torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
     upos = torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
-    check(lib().hc_csr_emit(ptr(sorted_keys), nkeys, ptr(n_valid), ptr(work), nnz, int(col_bits), int(nrows),
+    check(lib().hc_csr_emit(ptr(sorted_keys), nkeys, ptr(n_valid), ptr(work), nnz, int(col_bits), int(row0), int(nrows),
                             ptr(ukey), ptr(upos), ptr(row_ptr), ptr(col), ptr(cnt), stream_ptr()), "hc_csr_emit")
     return row_ptr, col, cnt
+
+
+def key_col_bits(nbins: int) -> int:
+    return max(1, int(nbins - 1).bit_length())
+
+
+def pairs_to_sorted_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                         check_bounds=True):
+    """pairs -> (row << col_bits | col) keys, both orientations, radix-sorted; padding keys
+    (dropped pairs) sort last.  Returns (sorted_keys, free_buffer, n_valid device scalar)."""
+    dev = pairs.device
+    col_bits = key_col_bits(nbins)
+    keys = torch.empty(2 * max(pairs.n, 1), dtype=torch.int64, device=dev)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+    oob = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().hc_pairs_to_keys(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2), pairs.n, int(res),
+                                 ptr(start), ptr(chrom_bins), int(start.numel()), int(bool(cis_only)), col_bits,
+                                 ptr(keys), ptr(n_valid), ptr(oob), stream_ptr()), "hc_pairs_to_keys")
+    if check_bounds:
+        _raise_oob(oob, "genome-wide")
+    keys = keys[:2 * pairs.n]
+    skeys, free = sort_keys_u64(keys, 2 * col_bits) if pairs.n else (keys, None)
+    return skeys, free, n_valid
 
 
 def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
@@ -278,7 +322,7 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
     """Binning through the sort path (north_star kernel (a)): every pair becomes one or two
     (row, col) keys, the keys are radix-sorted and run-length reduced into a symmetric CSR."""
     dev = pairs.device
-    col_bits = max(1, int(nbins - 1).bit_length())
+    col_bits = key_col_bits(nbins)
     keys = torch.empty(2 * max(pairs.n, 1), dtype=torch.int64, device=dev)
     n_valid = torch.zeros(1, dtype=torch.int64, device=dev)
     oob = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -297,17 +341,17 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
 
 def csr_upper_records(csr: SymCsr):
     """Upper-triangular (bin1, bin2, count) int32 device tensors of the local rows, row-major
-    (bin1 is LOCAL to the row block; add csr.row0 for global bins)."""
+    (global bin indices)."""
     dev = csr.device
     out_ptr = torch.empty(csr.nloc + 1, dtype=torch.int64, device=dev)
-    check(lib().hc_csr_upper_count(ptr(csr.row_ptr), ptr(csr.col), csr.nloc, ptr(out_ptr), stream_ptr()),
+    check(lib().hc_csr_upper_count(ptr(csr.row_ptr), ptr(csr.col), csr.row0, csr.nloc, ptr(out_ptr), stream_ptr()),
           "hc_csr_upper_count")
     n = int(out_ptr[-1].item())
     b1 = torch.empty(n, dtype=torch.int32, device=dev)
     b2 = torch.empty(n, dtype=torch.int32, device=dev)
     v = torch.empty(n, dtype=torch.int32, device=dev)
     if n:
-        check(lib().hc_csr_upper_emit(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.nloc, ptr(out_ptr),
+        check(lib().hc_csr_upper_emit(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.row0, csr.nloc, ptr(out_ptr),
                                       ptr(b1), ptr(b2), ptr(v), stream_ptr()), "hc_csr_upper_emit")
     return b1, b2, v
 

@@ -113,7 +113,7 @@ def bin_traditional(pairs: PairColumns, genome: dict, wholeRes, localRes, device
         whole[res] = (bins, W)
     for res in localRes:
         L = DenseBatch([genome[c] // res + 1 for c in order], dev)   # matrixBuilding.py:564
-        kernels.bin_pairs_local(pairs, res, L)
+        kernels.bin_pairs_local_partitioned(pairs, res, L)            # freshly zeroed tiles: symmetric on entry
         local[res] = L
     return whole, local
 
@@ -319,7 +319,7 @@ def WholeCsrToSparseDict(Bins, csr):
     intra blocks keyed 'c' (upper triangle), inter blocks 'c1_c2' (c1 before c2), block-local
     coordinates, row-major order inside each block."""
     b1, b2, v = (t.cpu().numpy() for t in kernels.csr_upper_records(csr))
-    b1 = b1.astype(np.int64) + csr.row0
+    b1 = b1.astype(np.int64)
     order = Sort_Chromosomes(Bins.keys())
     off = chrom_offsets_from_bins(Bins)
     ca = np.searchsorted(off, b1, side="right") - 1

@@ -332,3 +332,37 @@ def test_two_step_sizes_vs_oracle(mb, n, seed):
     check_matrix(out[1], ref[1], "n=%d PM" % n)
     np.testing.assert_allclose(out[0], out[0].T, rtol=1e-12)   # symmetric
     np.testing.assert_allclose(out[0].mean(), mm.mean(), rtol=1e-9)  # rescaled to the raw mean
+
+
+# ---------------------------------------------------------------------------------------
+# partitioned binning (radix partition by chromosome + L2-resident accumulation + mirror)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,res,mode", [(0, 40000, 0), (3, 40000, 0), (2049, 40000, 0), (300_000, 40000, 0),
+                                        (300_000, 7919, 0), (100_000, 40000, 1)])
+def test_partitioned_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
+    from hichap_master_b200 import kernels
+    from hichap_master_b200.device import DenseBatch, PairColumns
+    genome = {c: l for c, l in SMALL_GENOME.items() if c != "M"}
+    order = list(genome)
+    c1, p1, c2, p2 = synth.genome_pairs(genome, order, max(n, 1), 31, trans_frac=0.2)
+    c1, p1, c2, p2 = c1[:n].copy(), p1[:n], c2[:n].copy(), p2[:n]
+    if n > 10:
+        c1[::17] = -1                                  # filtered chromosome
+    rng = np.random.default_rng(2)
+    mark = rng.integers(0, 4, size=n).astype(np.uint8)
+    sizes = [genome[c] // res + 1 for c in order]
+    pc = PairColumns(c1, p1, c2, p2, mark)
+    A = DenseBatch(sizes, cuda_device); B = DenseBatch(sizes, cuda_device)
+    kernels.bin_pairs_local(pc, res, A, mode)
+    kernels.bin_pairs_local_partitioned(pc, res, B, mode)
+    keep = (c1 >= 0) & (c2 >= 0) & ((mark == 0) | (mode == 0))
+    exp = ho.bin_local_dense(c1[keep], p1[keep], c2[keep], p2[keep], sizes, res)
+    for i in range(len(sizes)):
+        a, b = A.to_numpy(i), B.to_numpy(i)
+        assert np.array_equal(a, exp[i]) and np.array_equal(b, exp[i]), (i, sizes[i])
+    assert int(B.buf.sum().item()) == int(A.buf.sum().item())   # nothing landed in the row padding
+    # out-of-range positions raise like the direct kernel
+    bad = PairColumns(np.array([0], np.int32), np.array([2_000_000_000], np.int32), np.array([0], np.int32),
+                      np.array([5], np.int32))
+    with pytest.raises(IndexError):
+        kernels.bin_pairs_local_partitioned(bad, res, DenseBatch(sizes, cuda_device))
