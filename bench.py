@@ -208,12 +208,14 @@ def run_ours(args):
             b.record(); torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
         t_zero = ev_time(lambda: stage.batch.buf.zero_())
-        t_bin = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local(pairs, RES, stage.batch, check_bounds=False))) - t_zero
+        t_bin_direct = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local(pairs, RES, stage.batch, check_bounds=False))) - t_zero
+        t_bin = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local_partitioned(
+            pairs, RES, stage.batch, check_bounds=False, work=stage.bin_work))) - t_zero
         params = kernels.ice_params()
         t_filt = ev_time(lambda: kernels.ice_dense_filters(stage.batch, params))
         sq = float(sum(n * n for n in sizes))
         breakdown = {
-            "zero_tiles_ms": t_zero, "binning_ms": t_bin, "ice_filters_ms": t_filt, "ice_loop_ms": loop_ms,
+            "zero_tiles_ms": t_zero, "binning_ms": t_bin, "binning_direct_atomics_ms": t_bin_direct, "ice_filters_ms": t_filt, "ice_loop_ms": loop_ms,
             "binning_GBps": 16.0 * n_local / (t_bin * 1e6), "binning_Gpairs_per_s": n_local / (t_bin * 1e6),
             "ice_filters_GBps": 4.0 * sq / (t_filt * 1e6),
             "ice_iters": [int(i) for i in iters], "ice_iter_launches": n_iter_launches,

@@ -31,3 +31,28 @@ extern "C" int hc_init(void) {
     HC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     return HC_OK;
 }
+
+// dst += src (replicate merge of dense tiles, matrixBuilding.py:1700-1719)
+__global__ void __launch_bounds__(256) add_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, long long n) {
+    const long long nv = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
+        int4 a = reinterpret_cast<const int4*>(dst)[v];
+        const int4 b = ld_stream_v4(src + 4 * v);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        reinterpret_cast<int4*>(dst)[v] = a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - (nv << 2))) dst[(nv << 2) + threadIdx.x] += src[(nv << 2) + threadIdx.x];
+}
+
+extern "C" int hc_add_i32(int32_t* dst, const int32_t* src, int64_t n, void* stream) {
+    HC_REQUIRE(n >= 0, "n>=0");
+    if (n == 0) return HC_OK;
+    HC_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0, "16-byte alignment");
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = (long long)hc_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    add_i32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}

@@ -351,3 +351,8 @@ def ice_balance_sparse(csr, Bins, cis_only=False, ignore_diags=1, mad_max=5, min
                                           min_count=min_count, tol=tol, max_iters=max_iters,
                                           rescale_marginals=rescale_marginals)
     return bias.cpu().numpy(), stats
+
+
+# drivers (replicate loop, merge, stores): same names as the reference, defined in construction.py
+from .construction import (Check_Bed, HaplotypeMatrixBuilding, HaplotypeMatrixConstruction, Merge_beds,  # noqa: E402,F401
+                           TraditionalMatrixConstruction)

@@ -76,6 +76,9 @@ int hc_bin_pairs_local_partitioned(const int32_t* c1, const int32_t* p1, const i
                                    const int32_t* h_mat_n, unsigned long long* oob, void* work,
                                    void* stream);
 
+/* dst[i] += src[i]: replicate merge of dense tiles (matrixBuilding.py:1700-1719). */
+int hc_add_i32(int32_t* dst, const int32_t* src, int64_t n, void* stream);
+
 /* Genome-wide ("whole") matrix: replaces matrixBuilding.py:582-592 (and :831-841, :1144-1151,
  * :1182-1189, :1217-1221, :1239-1243, :1285-1293).  bin1 = p1/res + start1[c1],
  * bin2 = p2/res + start2[c2]; start tables are device int64[nchrom].  HC_BIN_ONESIDED only
