@@ -209,7 +209,7 @@ def run_ours(args):
             return a.elapsed_time(b) / reps
         t_zero = ev_time(lambda: stage.batch.buf.zero_())
         t_bin_direct = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local(pairs, RES, stage.batch, check_bounds=False))) - t_zero
-        t_bin = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local_partitioned(
+        t_bin = ev_time(lambda: (stage.batch.buf.zero_(), kernels.bin_pairs_local_banded(
             pairs, RES, stage.batch, check_bounds=False, work=stage.bin_work))) - t_zero
         params = kernels.ice_params()
         t_filt = ev_time(lambda: kernels.ice_dense_filters(stage.batch, params))

@@ -45,9 +45,9 @@ SIGNATURES = {
     "hc_last_error": (C.c_char_p, []),
     "hc_launch_count": (C.c_int64, []),
     "hc_bin_pairs_local": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P]),
-    "hc_bin_part_work_bytes": (C.c_int64, [_I64, _I32]),
-    "hc_bin_pairs_local_partitioned": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32,
-                                                 C.POINTER(_I32), _P, _P, _P]),
+    "hc_bin_band_work_bytes": (C.c_int64, [_I64, _I32]),
+    "hc_bin_pairs_local_banded": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _I32,
+                                            C.POINTER(_I32), _I32, _P, _P, _P]),
     "hc_add_i32": (C.c_int, [_P, _P, _I64, _P]),
     "hc_bin_pairs_whole": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _I64, _P, _P]),
     "hc_dense_nonzero_count": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),

@@ -24,7 +24,7 @@ __device__ __forceinline__ bool mode_accepts(int mode, int mk) {
 }
 
 template <bool WHOLE>
-__device__ __forceinline__ void apply_pair(int c1, int p1, int c2, int p2, int mk, uint32_t res, int mode,
+__device__ __forceinline__ void apply_pair(int c1, int p1, int c2, int p2, int mk, FastDiv res, int mode,
                                            int32_t* __restrict__ mats, const int64_t* __restrict__ t0,
                                            const int64_t* __restrict__ t1, const int32_t* __restrict__ mat_n,
                                            const int32_t* __restrict__ mat_ld, int nchrom, int64_t whole_ld,
@@ -33,7 +33,7 @@ __device__ __forceinline__ void apply_pair(int c1, int p1, int c2, int p2, int m
     if (!mode_accepts(mode, mk)) return;
     if ((!WHOLE || mode == HC_BIN_ONESIDED) && c1 != c2) return;     // cis only
     if (p1 < 0 || p2 < 0) { if (oob) atomicAdd(oob, 1ull); return; }
-    int64_t b1 = (uint32_t)p1 / res, b2 = (uint32_t)p2 / res;
+    int64_t b1 = fast_div((uint32_t)p1, res), b2 = fast_div((uint32_t)p2, res);
     int32_t* M;
     int64_t ld, n;
     if (WHOLE) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ void apply_pair(int c1, int p1, int c2, int p2, int m
 
 template <bool WHOLE>
 __global__ void __launch_bounds__(BIN_THREADS)
-bin_pairs_kernel(PairCols in, int64_t npairs, uint32_t res, int mode, int32_t* __restrict__ mats,
+bin_pairs_kernel(PairCols in, int64_t npairs, FastDiv res, int mode, int32_t* __restrict__ mats,
                  const int64_t* __restrict__ t0, const int64_t* __restrict__ t1,
                  const int32_t* __restrict__ mat_n, const int32_t* __restrict__ mat_ld, int nchrom,
                  int64_t whole_ld, int32_t whole_n, unsigned long long* oob) {
@@ -152,125 +152,85 @@ row_nonzero_extract_kernel(const T* __restrict__ M, int64_t ld, int nrows, int n
     }
 }
 
-// ---- partitioned binning: radix partition by chromosome -> L2-resident accumulation --------
-// The direct kernel above is bound by DRAM read-modify-write traffic: random += 1 over 1.2 GB of
-// tiles misses L2 on almost every update (ncu: 31 GB of DRAM traffic for 6.4 GB of pairs).
-// Here the pairs are first partitioned by chromosome into packed (min_bin << 16 | max_bin) keys
-// (one streaming pass: 16 B read + 4 B written per pair); the keys are then accumulated into the
-// UPPER triangles bucket after bucket by persistent CTAs walking the key array in order, so the
-// tile being updated stays in L2; a final tile-transpose pass mirrors upper -> lower.
-constexpr int PART_THREADS = 256;
-constexpr int PART_ITEMS = 8;                      // pairs per thread per tile
-constexpr int PART_TILE = PART_THREADS * PART_ITEMS;
-constexpr int PART_MAX_BUCKETS = 256;
+__device__ __forceinline__ int batch_problem(const int64_t* __restrict__ bin_off, int nprob, int64_t g) {
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (bin_off[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
 
-struct PartArgs {
-    PairCols in; long long npairs; uint32_t res; int mode; int nchrom;
-    const int32_t* mat_n;
-    unsigned long long* bucket_count;   // [nchrom]   accepted pairs per chromosome
-    unsigned long long* bucket_start;   // [nchrom+1] exclusive scan
-    unsigned long long* cursor;         // [nchrom]   running fill of each bucket
-    uint32_t* keys;                     // [accepted] packed keys grouped by chromosome
+// ---- banded binning: near-diagonal updates land in an L2-resident band accumulator --------
+// The direct kernel above is bound by random DRAM read-modify-write: += 1 scattered over 1.2 GB of
+// tiles misses L2 on almost every update (ncu, profiles/r1a: 31 GB of DRAM traffic for 6.4 GB of
+// pairs, 13.7 ms).  Hi-C contacts concentrate near the diagonal (P(s) ~ 1/s), so here each pair
+// updates only the UPPER triangle, and pairs whose bins are fewer than BW apart go to a compact
+// band accumulator band[global_row][d] (nbins x BW int32: 39 MB at 40 kb with BW = 128) that
+// stays resident in the 126 MB L2; only the far pairs touch the big tiles.  A merge pass adds
+// the band into the tiles (coalesced 512-byte row segments) and a tile-transpose pass mirrors
+// upper -> lower.  (A two-pass radix partition by chromosome / row block was measured first --
+// profiles/r1c, r1d -- and lost to this single pass.)
+struct BandArgs {
+    PairCols in; long long npairs; FastDiv res; int mode; int nchrom;
+    int32_t* mats; const int64_t* mat_off; const int32_t* mat_n; const int32_t* mat_ld;
+    const int64_t* bin_off;              // global row offset of each chromosome
+    int32_t* band; int bw_shift;         // band[(global_row << bw_shift) + d], d < (1 << bw_shift)
     unsigned long long* oob;
 };
 
-// -1: dropped (filtered chromosome / trans / mark); -2: out of range; else chromosome + key
-__device__ __forceinline__ int classify_pair(const PartArgs& a, long long i, uint32_t* key) {
-    const int c1 = a.in.c1[i], c2 = a.in.c2[i];
-    if (c1 < 0 || c1 != c2 || c1 >= a.nchrom) return -1;
-    const int mk = a.in.mark ? a.in.mark[i] : 0;
-    if (!mode_accepts(a.mode, mk)) return -1;
-    const int p1 = a.in.p1[i], p2 = a.in.p2[i];
-    if (p1 < 0 || p2 < 0) return -2;
-    const uint32_t b1 = (uint32_t)p1 / a.res, b2 = (uint32_t)p2 / a.res, n = (uint32_t)a.mat_n[c1];
-    if (b1 >= n || b2 >= n) return -2;
-    *key = (min(b1, b2) << 16) | max(b1, b2);
-    return c1;
+__device__ __forceinline__ void band_apply(const BandArgs& a, int c1, int p1, int c2, int p2, int mk,
+                                           unsigned long long& my_oob) {
+    if (c1 < 0 || c1 != c2 || c1 >= a.nchrom) return;
+    if (!mode_accepts(a.mode, mk)) return;
+    if (p1 < 0 || p2 < 0) { ++my_oob; return; }
+    const uint32_t b1 = fast_div((uint32_t)p1, a.res), b2 = fast_div((uint32_t)p2, a.res), n = (uint32_t)a.mat_n[c1];
+    if (b1 >= n || b2 >= n) { ++my_oob; return; }
+    const uint32_t lo = min(b1, b2), d = max(b1, b2) - lo;
+    if ((d >> a.bw_shift) == 0) atomicAdd(a.band + (((a.bin_off[c1] + lo) << a.bw_shift) + d), 1);
+    else atomicAdd(a.mats + a.mat_off[c1] + (int64_t)lo * a.mat_ld[c1] + (lo + d), 1);
 }
 
-template <bool SCATTER>
-__global__ void __launch_bounds__(PART_THREADS) bin_partition_kernel(PartArgs a) {
-    __shared__ unsigned int s_cnt[PART_MAX_BUCKETS];
-    __shared__ unsigned long long s_base[PART_MAX_BUCKETS];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const long long ntiles = (a.npairs + PART_TILE - 1) / PART_TILE;
+__global__ void __launch_bounds__(BIN_THREADS) bin_pairs_band_kernel(BandArgs a) {
+    const int64_t nvec = a.npairs / PAIRS_PER_THREAD;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long my_oob = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i < a.nchrom; i += PART_THREADS) s_cnt[i] = 0;
-        __syncthreads();
-        uint32_t key[PART_ITEMS];
-        int bucket[PART_ITEMS];
-        unsigned rank[PART_ITEMS];
-#pragma unroll
-        for (int it = 0; it < PART_ITEMS; ++it) {
-            const long long i = tile * PART_TILE + it * PART_THREADS + threadIdx.x;   // coalesced
-            key[it] = 0;
-            bucket[it] = i < a.npairs ? classify_pair(a, i, &key[it]) : -1;
-            if (bucket[it] == -2) ++my_oob;
-            // warp-aggregated rank: one shared-memory atomic per distinct chromosome per warp
-            const int bk = bucket[it] >= 0 ? bucket[it] : PART_MAX_BUCKETS + lane;
-            const unsigned m = __match_any_sync(0xffffffffu, bk);
-            unsigned base = 0;
-            const int leader = __ffs(m) - 1;
-            if (bucket[it] >= 0 && lane == leader) base = atomicAdd(&s_cnt[bucket[it]], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            rank[it] = base + __popc(m & lt);
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < a.nchrom; c += PART_THREADS) {
-            const unsigned n = s_cnt[c];
-            if (!SCATTER) { if (n) atomicAdd(&a.bucket_count[c], (unsigned long long)n); }
-            else s_base[c] = a.bucket_start[c] + (n ? atomicAdd(&a.cursor[c], (unsigned long long)n) : 0ull);
-        }
-        if (SCATTER) {
-            __syncthreads();
-#pragma unroll
-            for (int it = 0; it < PART_ITEMS; ++it)
-                if (bucket[it] >= 0) a.keys[s_base[bucket[it]] + rank[it]] = key[it];
-        }
-        __syncthreads();
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const int4 c1 = ld_stream_v4(a.in.c1 + 4 * v), p1 = ld_stream_v4(a.in.p1 + 4 * v);
+        const int4 c2 = ld_stream_v4(a.in.c2 + 4 * v), p2 = ld_stream_v4(a.in.p2 + 4 * v);
+        uint32_t mk = 0;
+        if (a.in.mark) mk = *reinterpret_cast<const uint32_t*>(a.in.mark + 4 * v);
+        band_apply(a, c1.x, p1.x, c2.x, p2.x, mk & 255, my_oob);
+        band_apply(a, c1.y, p1.y, c2.y, p2.y, (mk >> 8) & 255, my_oob);
+        band_apply(a, c1.z, p1.z, c2.z, p2.z, (mk >> 16) & 255, my_oob);
+        band_apply(a, c1.w, p1.w, c2.w, p2.w, (mk >> 24) & 255, my_oob);
     }
-    if (!SCATTER && a.oob) {
+    if (blockIdx.x == 0 && threadIdx.x < (int)(a.npairs - nvec * PAIRS_PER_THREAD)) {
+        const int64_t i = nvec * PAIRS_PER_THREAD + threadIdx.x;
+        band_apply(a, a.in.c1[i], a.in.p1[i], a.in.c2[i], a.in.p2[i], a.in.mark ? a.in.mark[i] : 0, my_oob);
+    }
+    if (a.oob) {
         my_oob = (unsigned long long)warp_sum_ll((long long)my_oob);
-        if (lane == 0 && my_oob) atomicAdd(a.oob, my_oob);
+        if ((threadIdx.x & 31) == 0 && my_oob) atomicAdd(a.oob, my_oob);
     }
 }
 
-__global__ void bin_partition_scan_kernel(PartArgs a) {
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int c = 0; c < a.nchrom; ++c) { a.bucket_start[c] = run; run += a.bucket_count[c]; a.cursor[c] = 0; }
-        a.bucket_start[a.nchrom] = run;
+// tiles[r][r + d] += band[r][d]: one warp per global row, coalesced on both sides
+__global__ void __launch_bounds__(256) band_merge_kernel(BandArgs a, int64_t nbins) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= nbins) return;
+    const int p = batch_problem(a.bin_off, a.nchrom, g);
+    const int r = (int)(g - a.bin_off[p]), n = a.mat_n[p], bw = 1 << a.bw_shift;
+    int32_t* row = a.mats + a.mat_off[p] + (int64_t)r * a.mat_ld[p] + r;
+    const int32_t* b = a.band + (g << a.bw_shift);
+    for (int d = lane; d < bw && r + d < n; d += 32) {
+        const int v = b[d];
+        if (v) row[d] += v;
     }
 }
 
-// persistent CTAs walk the grouped keys front to back: concurrently running CTAs update the same
-// one or two chromosomes, whose upper triangles fit L2
-__global__ void __launch_bounds__(256)
-bin_accumulate_kernel(const uint32_t* __restrict__ keys, const unsigned long long* __restrict__ bucket_start, int nchrom,
-                      int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off, const int32_t* __restrict__ mat_ld) {
-    const long long total = (long long)bucket_start[nchrom];
-    constexpr int CHUNK = 256 * 8;
-    for (long long base = (long long)blockIdx.x * CHUNK; base < total; base += (long long)gridDim.x * CHUNK) {
-        int c = 0;                                   // bucket of the chunk's first key (binary search)
-        {
-            int lo = 0, hi = nchrom - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)bucket_start[mid] <= base) lo = mid; else hi = mid - 1; }
-            c = lo;
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const long long i = base + it * 256 + threadIdx.x;
-            if (i < total) {
-                int cc = c;
-                while ((long long)bucket_start[cc + 1] <= i) ++cc;
-                const uint32_t k = keys[i];
-                atomicAdd(&mats[mat_off[cc] + (int64_t)(k >> 16) * mat_ld[cc] + (k & 0xffffu)], 1);
-            }
-        }
-    }
-}
+constexpr int PART_MAX_BUCKETS = 256;   // (bounds the by-value table of the mirror kernel)
 
 // lower = transpose(upper) for every matrix of the batch (32x32 tiles through shared memory)
 struct MirrorTab { int nprob; int start[PART_MAX_BUCKETS + 1]; };   // prefix of T_p(T_p+1)/2 tile pairs per matrix
@@ -310,15 +270,6 @@ mirror_upper_kernel(int32_t* __restrict__ mats, const int64_t* __restrict__ mat_
 
 // ---- whole batch at once: upper-triangular records in the reference's 24-byte layout ------
 struct Rec24 { long long bin1; long long bin2; double IF; };   // matrixBuilding.py:460-461 S_dtype
-
-__device__ __forceinline__ int batch_problem(const int64_t* __restrict__ bin_off, int nprob, int64_t g) {
-    int lo = 0, hi = nprob - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (bin_off[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 __global__ void __launch_bounds__(256)
 batch_triu_count_kernel(const int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off,
@@ -403,54 +354,54 @@ extern "C" int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const in
     HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
     PairCols in{c1, p1, c2, p2, mark};
     bin_pairs_kernel<false><<<bin_grid(npairs), BIN_THREADS, 0, (cudaStream_t)stream>>>(
-        in, npairs, (uint32_t)res, mode, mats, mat_off, nullptr, mat_n, mat_ld, nchrom, 0, 0, oob);
+        in, npairs, make_fast_div((uint32_t)res), mode, mats, mat_off, nullptr, mat_n, mat_ld, nchrom, 0, 0, oob);
     HC_LAUNCH_CHECK();
     return HC_OK;
 }
 
-// Partitioned variant of hc_bin_pairs_local for SYMMETRIC modes on matrices that are symmetric on
-// entry (e.g. freshly zeroed): same result, ~3x less DRAM traffic.  work: hc_bin_part_work_bytes.
-extern "C" int64_t hc_bin_part_work_bytes(int64_t npairs, int32_t nchrom) {
-    return (int64_t)sizeof(uint32_t) * (npairs > 0 ? npairs : 1) + (int64_t)sizeof(unsigned long long) * (3 * (int64_t)nchrom + 2) + 64;
+// Banded variant of hc_bin_pairs_local for the SYMMETRIC modes on matrices that are symmetric on
+// entry (e.g. freshly zeroed): same result, most atomics resolved in L2.
+extern "C" int64_t hc_bin_band_work_bytes(int64_t nbins, int32_t band_width) {
+    return (int64_t)sizeof(int32_t) * (nbins > 0 ? nbins : 1) * band_width;
 }
 
-extern "C" int hc_bin_pairs_local_partitioned(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
-                                              const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
-                                              int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
-                                              const int32_t* mat_ld, int32_t nchrom, const int32_t* h_mat_n,
-                                              unsigned long long* oob, void* work, void* stream) {
+extern "C" int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                                         const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                                         int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                         const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
+                                         const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
+                                         void* work, void* stream) {
     HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0, "npairs>=0, res>0, nchrom>0");
-    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mode == HC_BIN_SYM_BOTH, "partitioned binning is for the symmetric modes");
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mode == HC_BIN_SYM_BOTH, "banded binning is for the symmetric modes");
     HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     HC_REQUIRE(nchrom <= PART_MAX_BUCKETS && h_mat_n != nullptr, "at most 256 chromosomes; h_mat_n");
+    HC_REQUIRE(band_width >= 32 && band_width <= 1024 && (band_width & (band_width - 1)) == 0, "band_width: power of two in [32,1024]");
     MirrorTab mtab;
     mtab.nprob = nchrom;
     mtab.start[0] = 0;
+    int64_t nbins = 0;
     for (int p = 0; p < nchrom; ++p) {
-        HC_REQUIRE(h_mat_n[p] >= 0 && h_mat_n[p] <= 65536, "matrix side must be <= 65536 bins");
+        HC_REQUIRE(h_mat_n[p] >= 0, "matrix side");
+        nbins += h_mat_n[p];
         const long long T = (h_mat_n[p] + 31) / 32;
         const long long nxt = mtab.start[p] + T * (T + 1) / 2;
         HC_REQUIRE(nxt < (1ll << 31), "too many tiles");
         mtab.start[p + 1] = (int)nxt;
     }
-    if (npairs == 0) return HC_OK;
+    if (npairs == 0 || nbins == 0) return HC_OK;
+    HC_REQUIRE(aligned16(c1) && aligned16(p1) && aligned16(c2) && aligned16(p2), "pair columns must be 16-byte aligned");
+    HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    PartArgs a;
-    a.in = PairCols{c1, p1, c2, p2, mark}; a.npairs = npairs; a.res = (uint32_t)res; a.mode = mode; a.nchrom = nchrom;
-    a.mat_n = mat_n; a.oob = oob;
-    unsigned long long* tab = reinterpret_cast<unsigned long long*>(work);
-    a.bucket_count = tab; a.bucket_start = tab + nchrom; a.cursor = tab + 2 * nchrom + 1;
-    a.keys = reinterpret_cast<uint32_t*>(tab + 3 * nchrom + 2);
-    HC_CUDA(cudaMemsetAsync(tab, 0, sizeof(unsigned long long) * (3 * (size_t)nchrom + 2), s));
-    const long long ntiles = (npairs + PART_TILE - 1) / PART_TILE;
-    const int grid = (int)std::min<long long>(ntiles, (long long)hc_num_sms() * 8);
-    bin_partition_kernel<false><<<grid, PART_THREADS, 0, s>>>(a);
+    BandArgs a;
+    a.in = PairCols{c1, p1, c2, p2, mark}; a.npairs = npairs; a.res = make_fast_div((uint32_t)res); a.mode = mode;
+    a.nchrom = nchrom; a.mats = mats; a.mat_off = mat_off; a.mat_n = mat_n; a.mat_ld = mat_ld; a.bin_off = bin_off;
+    a.band = reinterpret_cast<int32_t*>(work); a.oob = oob;
+    a.bw_shift = 0;
+    while ((1 << a.bw_shift) < band_width) ++a.bw_shift;
+    HC_CUDA(cudaMemsetAsync(a.band, 0, sizeof(int32_t) * (size_t)nbins * band_width, s));
+    bin_pairs_band_kernel<<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
     HC_LAUNCH_CHECK();
-    bin_partition_scan_kernel<<<1, 32, 0, s>>>(a);
-    HC_LAUNCH_CHECK();
-    bin_partition_kernel<true><<<grid, PART_THREADS, 0, s>>>(a);
-    HC_LAUNCH_CHECK();
-    bin_accumulate_kernel<<<hc_num_sms() * 8, 256, 0, s>>>(a.keys, a.bucket_start, nchrom, mats, mat_off, mat_ld);
+    band_merge_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, s>>>(a, nbins);
     HC_LAUNCH_CHECK();
     if (mtab.start[nchrom] > 0) {
         mirror_upper_kernel<<<mtab.start[nchrom], 256, 0, s>>>(mats, mat_off, mat_n, mat_ld, mtab);
@@ -471,7 +422,7 @@ extern "C" int hc_bin_pairs_whole(const int32_t* c1, const int32_t* p1, const in
     HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
     PairCols in{c1, p1, c2, p2, mark};
     bin_pairs_kernel<true><<<bin_grid(npairs), BIN_THREADS, 0, (cudaStream_t)stream>>>(
-        in, npairs, (uint32_t)res, mode, M, start1, start2, nullptr, nullptr, nchrom, ld, total, oob);
+        in, npairs, make_fast_div((uint32_t)res), mode, M, start1, start2, nullptr, nullptr, nchrom, ld, total, oob);
     HC_LAUNCH_CHECK();
     return HC_OK;
 }

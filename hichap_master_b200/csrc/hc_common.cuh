@@ -43,7 +43,25 @@ static inline int hc_num_sms() {
     return sms;
 }
 
+// Unsigned 32-bit division by a run-time invariant (bin = position / resolution) as a multiply-high
+// and two shifts (Granlund & Montgomery, "Division by invariant integers using multiplication").
+struct FastDiv { uint32_t m; int s1, s2; };
+static inline FastDiv make_fast_div(uint32_t d) {
+    int l = 0;
+    while (l < 32 && (1ull << l) < d) ++l;                       // ceil(log2 d)
+    FastDiv f;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 1 ? l - 1 : 0;
+    return f;
+}
+
 // ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, FastDiv f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 __device__ __forceinline__ int4 ld_stream_v4(const int32_t* p) {
     // 128-bit streaming load: read-only path, do not allocate in L1 (data is touched once)
     int4 r;

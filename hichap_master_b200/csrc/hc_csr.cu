@@ -18,7 +18,7 @@ constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS;
 // ---- pairs -> keys ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pairs_to_keys_kernel(const int32_t* __restrict__ c1, const int32_t* __restrict__ p1, const int32_t* __restrict__ c2,
-                     const int32_t* __restrict__ p2, long long npairs, uint32_t res,
+                     const int32_t* __restrict__ p2, long long npairs, FastDiv res,
                      const int64_t* __restrict__ start, const int32_t* __restrict__ chrom_bins, int nchrom,
                      int cis_only, int col_bits, unsigned long long* __restrict__ keys,
                      unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ oob) {
@@ -29,8 +29,8 @@ pairs_to_keys_kernel(const int32_t* __restrict__ c1, const int32_t* __restrict__
         const int a = c1[i], b = c2[i];
         if (a >= 0 && b >= 0 && a < nchrom && b < nchrom && (!cis_only || a == b)) {
             const int x = p1[i], y = p2[i];
-            const long long ba = x >= 0 ? (long long)((uint32_t)x / res) : -1;
-            const long long bb = y >= 0 ? (long long)((uint32_t)y / res) : -1;
+            const long long ba = x >= 0 ? (long long)fast_div((uint32_t)x, res) : -1;
+            const long long bb = y >= 0 ? (long long)fast_div((uint32_t)y, res) : -1;
             if (ba < 0 || bb < 0 || ba >= chrom_bins[a] || bb >= chrom_bins[b]) {
                 ++local_oob;
             } else {
@@ -195,7 +195,7 @@ extern "C" int hc_pairs_to_keys(const int32_t* c1, const int32_t* p1, const int3
     const long long cap = (long long)hc_num_sms() * 16;
     if (blocks > cap) blocks = cap;
     pairs_to_keys_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        c1, p1, c2, p2, npairs, (uint32_t)res, start, chrom_bins, nchrom, cis_only, col_bits, keys, n_valid, oob);
+        c1, p1, c2, p2, npairs, make_fast_div((uint32_t)res), start, chrom_bins, nchrom, cis_only, col_bits, keys, n_valid, oob);
     HC_LAUNCH_CHECK();
     return HC_OK;
 }

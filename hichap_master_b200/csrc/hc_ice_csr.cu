@@ -14,7 +14,7 @@
 #include <vector>
 #include "hc_common.cuh"
 
-int hc_nccl_allreduce_f64(void* comm, double* buf, size_t count, cudaStream_t s);  // hc_nccl.cu
+int hc_nccl_allreduce_f64(void* comm, const double* send, double* recv, size_t count, cudaStream_t s);  // hc_nccl.cu
 
 namespace {
 
@@ -227,7 +227,7 @@ extern "C" int hc_ice_csr_marginals(const int64_t* row_ptr, const int32_t* col, 
 }
 
 extern "C" int64_t hc_ice_csr_work_bytes(int64_t nbins, int32_t nprob) {
-    return (int64_t)sizeof(double) * (nbins + 3ll * nprob * STAT_SLICES) + sizeof(int32_t) * (nprob + 4ll) + 64;
+    return (int64_t)sizeof(double) * (2 * nbins + 3ll * nprob * STAT_SLICES) + sizeof(int32_t) * (nprob + 4ll) + 64;
 }
 
 // Balance to convergence.  bias: full-length vector (in: initial bias from the filters; out:
@@ -246,12 +246,15 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
     if (nbins == 0) return HC_OK;
 
     double* marg = reinterpret_cast<double*>(work);
-    double* part_sum = marg + nbins;
+    // sharded: the stream kernel writes the local rows of marg_local (zero elsewhere, zeroed once)
+    // and the allreduce sums the ranks' vectors into marg; single GPU: both are the same buffer
+    double* marg_local = nccl_comm ? marg + nbins : marg;
+    double* part_sum = marg + 2 * nbins;
     double* part_var = part_sum + (size_t)nprob * STAT_SLICES;
     long long* part_cnt = reinterpret_cast<long long*>(part_var + (size_t)nprob * STAT_SLICES);
     int32_t* done_at = reinterpret_cast<int32_t*>(part_cnt + (size_t)nprob * STAT_SLICES);
     int32_t* n_done = done_at + nprob;
-    HC_CUDA(cudaMemsetAsync(marg, 0, sizeof(double) * nbins, s));
+    HC_CUDA(cudaMemsetAsync(marg, 0, sizeof(double) * 2 * nbins, s));
     HC_CUDA(cudaMemsetAsync(done_at, 0, sizeof(int32_t) * (nprob + 1), s));
 
     // empty problems (no bins) are done from the start
@@ -295,11 +298,11 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
     for (int k = 1; k <= P->max_iters; ++k) {
         if (nloc > 0) {
             ice_csr_stream_kernel<false><<<stream_grid(), 256, 0, s>>>(A, bias, P->ignore_diags, bin_off, nprob, done_at,
-                                                                     k, marg, nullptr);
+                                                                     k, marg_local, nullptr);
             hc_count_launch(); ++launches;
         }
         if (nccl_comm) {
-            rc = hc_nccl_allreduce_f64(nccl_comm, marg, (size_t)nbins, s);
+            rc = hc_nccl_allreduce_f64(nccl_comm, marg_local, marg, (size_t)nbins, s);
             if (rc != HC_OK) break;
         }
         st.k = k;

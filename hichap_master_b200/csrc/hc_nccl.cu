@@ -46,10 +46,10 @@ int nccl_fail(const char* what, ncclResult_t r) {
 
 }  // namespace
 
-int hc_nccl_allreduce_f64(void* comm, double* buf, size_t count, cudaStream_t s) {
+int hc_nccl_allreduce_f64(void* comm, const double* send, double* recv, size_t count, cudaStream_t s) {
     NcclApi& a = api();
     if (!a.ok) { hc_set_error("libnccl.so.2 not available"); return HC_ERR_NCCL; }
-    ncclResult_t r = a.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, (ncclComm_t)comm, s);
+    ncclResult_t r = a.AllReduce(send, recv, count, kNcclFloat64, kNcclSum, (ncclComm_t)comm, s);
     return r == 0 ? HC_OK : nccl_fail("ncclAllReduce", r);
 }
 
@@ -86,5 +86,5 @@ extern "C" int hc_nccl_comm_destroy(void* comm) {
 }
 
 extern "C" int hc_nccl_allreduce_sum_f64(void* comm, double* buf, int64_t count, void* stream) {
-    return hc_nccl_allreduce_f64(comm, buf, (size_t)count, (cudaStream_t)stream);
+    return hc_nccl_allreduce_f64(comm, buf, buf, (size_t)count, (cudaStream_t)stream);
 }

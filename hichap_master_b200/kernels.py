@@ -5,6 +5,7 @@ NumPy-out functions live in ``matrixBuilding.py`` and are built from these.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -44,22 +45,26 @@ def bin_pairs_local(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.H
         _raise_oob(oob, "intra-chromosomal")
 
 
-def bin_pairs_local_partitioned(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
-                                check_bounds=True, work=None):
+def bin_pairs_local_banded(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
+                           check_bounds=True, work=None, band_width=None):
     """``bin_pairs_local`` for the symmetric modes on matrices that are symmetric on entry
-    (freshly zeroed tiles): radix partition by chromosome, L2-resident accumulation of the upper
-    triangles, mirror.  Falls back to the direct kernel outside its limits."""
-    if len(batch) > 256 or max(batch.sizes) > 65536 or mode == _abi.HC_BIN_ONESIDED:
-        return bin_pairs_local(pairs, res, batch, mode, check_bounds)
+    (freshly zeroed tiles): upper-triangle-only updates with an L2-resident near-diagonal band
+    accumulator, band merge, mirror.  Falls back to the direct kernel outside its limits.
+    Returns the work buffer (reusable)."""
+    if len(batch) > 256 or mode == _abi.HC_BIN_ONESIDED or batch.nbins == 0:
+        bin_pairs_local(pairs, res, batch, mode, check_bounds)
+        return work
+    if band_width is None:
+        band_width = int(os.environ.get("HC_BIN_BAND", "128"))
     oob = _oob_counter(batch.device)
-    nbytes = int(lib().hc_bin_part_work_bytes(pairs.n, len(batch)))
+    nbytes = int(lib().hc_bin_band_work_bytes(batch.nbins, band_width))
     if work is None or work.numel() < nbytes:
         work = torch.empty(nbytes, dtype=torch.uint8, device=batch.device)
-    check(lib().hc_bin_pairs_local_partitioned(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
-                                               ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(batch.buf),
-                                               ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld), len(batch),
-                                               batch.h_mat_n, ptr(oob), ptr(work), stream_ptr()),
-          "hc_bin_pairs_local_partitioned")
+    check(lib().hc_bin_pairs_local_banded(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
+                                          ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(batch.buf),
+                                          ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld),
+                                          ptr(batch.bin_off), len(batch), batch.h_mat_n, band_width, ptr(oob),
+                                          ptr(work), stream_ptr()), "hc_bin_pairs_local_banded")
     if check_bounds:
         _raise_oob(oob, "intra-chromosomal")
     return work

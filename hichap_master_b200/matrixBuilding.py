@@ -113,7 +113,7 @@ def bin_traditional(pairs: PairColumns, genome: dict, wholeRes, localRes, device
         whole[res] = (bins, W)
     for res in localRes:
         L = DenseBatch([genome[c] // res + 1 for c in order], dev)   # matrixBuilding.py:564
-        kernels.bin_pairs_local_partitioned(pairs, res, L)            # freshly zeroed tiles: symmetric on entry
+        kernels.bin_pairs_local_banded(pairs, res, L)            # freshly zeroed tiles: symmetric on entry
         local[res] = L
     return whole, local
 
@@ -251,8 +251,8 @@ def GenomeWideMatrixCorrection(Bins_Pos, Hap_Bins_Pos, T_M, H_M):
     concatenated in sorted chromosome order and repeated for the P half; H/alpha ->
     sum-symmetrise -> Correct_VC(2/3) -> rescale to the raw mean."""
     dev = require_cuda()
-    Tb = DenseBatch.from_numpy([np.asarray(T_M)])
-    Hb = DenseBatch.from_numpy([np.asarray(H_M)])
+    Tb = T_M if isinstance(T_M, DenseBatch) else DenseBatch.from_numpy([np.asarray(T_M)])
+    Hb = H_M if isinstance(H_M, DenseBatch) else DenseBatch.from_numpy([np.asarray(H_M)])
     n_h = Hb.sizes[0]
     alphas = {}
     for chro, (lo, hi) in Bins_Pos.items():

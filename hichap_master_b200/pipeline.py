@@ -38,7 +38,7 @@ class LocalStage:
         self.cols = [torch.empty(max(self.max_pairs, 4), dtype=torch.int32, device=self.dev) for _ in range(4)]
         self.weights_host = torch.empty(self.batch.nbins, dtype=torch.float64).pin_memory()
         self.pool = kernels.PinnedPool()
-        self.partitioned = True      # radix-partitioned binning (hc_bin_pairs_local_partitioned)
+        self.banded = True      # banded binning (hc_bin_pairs_local_banded)
         self.bin_work = None
 
     def upload(self, hp: HostPairs) -> PairColumns:
@@ -51,8 +51,8 @@ class LocalStage:
         """zero tiles -> bin -> [extract upper-triangular records] -> filters -> ICE."""
         b = self.batch
         b.buf.zero_()
-        if self.partitioned:
-            self.bin_work = kernels.bin_pairs_local_partitioned(pairs, res, b, check_bounds=False, work=self.bin_work)
+        if self.banded:
+            self.bin_work = kernels.bin_pairs_local_banded(pairs, res, b, check_bounds=False, work=self.bin_work)
         else:
             kernels.bin_pairs_local(pairs, res, b, check_bounds=False)
         recs = None

@@ -64,17 +64,18 @@ int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const int32_t* c2, 
                        void* stream);
 
 /* Same result as hc_bin_pairs_local for the SYMMETRIC modes when the matrices are symmetric on
- * entry (e.g. freshly zeroed), with ~3x less DRAM traffic: the pairs are radix-partitioned by
- * chromosome into packed keys, accumulated into the upper triangles while each tile is resident
- * in L2, then mirrored.  At most 256 chromosomes of at most 65536 bins (h_mat_n: host copy of the sides).
- * work: hc_bin_part_work_bytes(npairs, nchrom) bytes. */
-int64_t hc_bin_part_work_bytes(int64_t npairs, int32_t nchrom);
-int hc_bin_pairs_local_partitioned(const int32_t* c1, const int32_t* p1, const int32_t* c2,
-                                   const int32_t* p2, const uint8_t* mark, int64_t npairs, int32_t res,
-                                   int32_t mode, int32_t* mats, const int64_t* mat_off,
-                                   const int32_t* mat_n, const int32_t* mat_ld, int32_t nchrom,
-                                   const int32_t* h_mat_n, unsigned long long* oob, void* work,
-                                   void* stream);
+ * entry (e.g. freshly zeroed), with most updates resolved in L2: only the upper triangle is
+ * updated, pairs fewer than band_width bins apart go to a compact nbins x band_width accumulator
+ * (work: hc_bin_band_work_bytes) that stays L2-resident, then the band is merged into the tiles
+ * and the upper triangle mirrored.  bin_off: device int64[nchrom+1] concatenated bin offsets;
+ * h_mat_n: host copy of the sides; band_width: power of two in [32, 1024]. */
+int64_t hc_bin_band_work_bytes(int64_t nbins, int32_t band_width);
+int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                              const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                              int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                              const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
+                              const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
+                              void* work, void* stream);
 
 /* dst[i] += src[i]: replicate merge of dense tiles (matrixBuilding.py:1700-1719). */
 int hc_add_i32(int32_t* dst, const int32_t* src, int64_t n, void* stream);

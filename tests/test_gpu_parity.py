@@ -335,11 +335,11 @@ def test_two_step_sizes_vs_oracle(mb, n, seed):
 
 
 # ---------------------------------------------------------------------------------------
-# partitioned binning (radix partition by chromosome + L2-resident accumulation + mirror)
+# banded binning (upper-only updates, L2-resident near-diagonal band, merge, mirror)
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,res,mode", [(0, 40000, 0), (3, 40000, 0), (2049, 40000, 0), (300_000, 40000, 0),
                                         (300_000, 7919, 0), (100_000, 40000, 1)])
-def test_partitioned_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
+def test_banded_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
     from hichap_master_b200 import kernels
     from hichap_master_b200.device import DenseBatch, PairColumns
     genome = {c: l for c, l in SMALL_GENOME.items() if c != "M"}
@@ -354,7 +354,7 @@ def test_partitioned_binning_equals_direct_and_oracle(mb, cuda_device, n, res, m
     pc = PairColumns(c1, p1, c2, p2, mark)
     A = DenseBatch(sizes, cuda_device); B = DenseBatch(sizes, cuda_device)
     kernels.bin_pairs_local(pc, res, A, mode)
-    kernels.bin_pairs_local_partitioned(pc, res, B, mode)
+    kernels.bin_pairs_local_banded(pc, res, B, mode)
     keep = (c1 >= 0) & (c2 >= 0) & ((mark == 0) | (mode == 0))
     exp = ho.bin_local_dense(c1[keep], p1[keep], c2[keep], p2[keep], sizes, res)
     for i in range(len(sizes)):
@@ -365,4 +365,4 @@ def test_partitioned_binning_equals_direct_and_oracle(mb, cuda_device, n, res, m
     bad = PairColumns(np.array([0], np.int32), np.array([2_000_000_000], np.int32), np.array([0], np.int32),
                       np.array([5], np.int32))
     with pytest.raises(IndexError):
-        kernels.bin_pairs_local_partitioned(bad, res, DenseBatch(sizes, cuda_device))
+        kernels.bin_pairs_local_banded(bad, res, DenseBatch(sizes, cuda_device))
