@@ -239,6 +239,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args.pairs), "pairs": args.pairs, "bins": int(sum(sizes_all)),
                    "resolution": RES, "chromosomes": len(order),
                    "parallelism": "chromosomes LPT-sharded by N^2 over %d GPU(s), no collective" % world,
+                   "host_format": "pinned columns: chromosome uint8 + mid-point int32 per mate (10 B/pair)",
                    "l2": "inputs larger than L2 (%.1f GB pair columns, %.2f GB int32 tiles on rank 0)"
                          % (16e-9 * n_local, 4e-9 * stage.batch.numel)},
         "throughput_Mpairs_per_s": args.pairs / (ms_step * 1e3),

@@ -56,3 +56,34 @@ extern "C" int hc_add_i32(int32_t* dst, const int32_t* src, int64_t n, void* str
     HC_LAUNCH_CHECK();
     return HC_OK;
 }
+
+// chromosome ids travel over PCIe as uint8 (255 = filtered) and are widened on the device
+__global__ void __launch_bounds__(256) widen_u8_i32_kernel(const uint8_t* __restrict__ src, int32_t* __restrict__ dst, long long n) {
+    const long long nv = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += stride) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(src)[v];
+        int4 o;
+        o.x = (w & 255u) == 255u ? -1 : (int)(w & 255u);
+        o.y = ((w >> 8) & 255u) == 255u ? -1 : (int)((w >> 8) & 255u);
+        o.z = ((w >> 16) & 255u) == 255u ? -1 : (int)((w >> 16) & 255u);
+        o.w = (w >> 24) == 255u ? -1 : (int)(w >> 24);
+        reinterpret_cast<int4*>(dst)[v] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - (nv << 2))) {
+        const uint8_t b = src[(nv << 2) + threadIdx.x];
+        dst[(nv << 2) + threadIdx.x] = b == 255 ? -1 : (int)b;
+    }
+}
+
+extern "C" int hc_widen_u8_i32(const uint8_t* src, int32_t* dst, int64_t n, void* stream) {
+    HC_REQUIRE(n >= 0, "n>=0");
+    if (n == 0) return HC_OK;
+    HC_REQUIRE((reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "alignment");
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = (long long)hc_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    widen_u8_i32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}

@@ -180,14 +180,14 @@ struct BandArgs {
 };
 
 __device__ __forceinline__ void band_apply(const BandArgs& a, int c1, int p1, int c2, int p2, int mk,
-                                           unsigned long long& my_oob) {
+                                           unsigned long long& my_oob, uint64_t keep) {
     if (c1 < 0 || c1 != c2 || c1 >= a.nchrom) return;
     if (!mode_accepts(a.mode, mk)) return;
     if (p1 < 0 || p2 < 0) { ++my_oob; return; }
     const uint32_t b1 = fast_div((uint32_t)p1, a.res), b2 = fast_div((uint32_t)p2, a.res), n = (uint32_t)a.mat_n[c1];
     if (b1 >= n || b2 >= n) { ++my_oob; return; }
     const uint32_t lo = min(b1, b2), d = max(b1, b2) - lo;
-    if ((d >> a.bw_shift) == 0) atomicAdd(a.band + (((a.bin_off[c1] + lo) << a.bw_shift) + d), 1);
+    if ((d >> a.bw_shift) == 0) red_add_s32_hint(a.band + (((a.bin_off[c1] + lo) << a.bw_shift) + d), 1, keep);
     else atomicAdd(a.mats + a.mat_off[c1] + (int64_t)lo * a.mat_ld[c1] + (lo + d), 1);
 }
 
@@ -195,19 +195,20 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_band_kernel(BandArgs a)
     const int64_t nvec = a.npairs / PAIRS_PER_THREAD;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long my_oob = 0;
+    const uint64_t once = l2_policy_evict_first(), keep = l2_policy_evict_last();   // pairs stream through; the band stays
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const int4 c1 = ld_stream_v4(a.in.c1 + 4 * v), p1 = ld_stream_v4(a.in.p1 + 4 * v);
-        const int4 c2 = ld_stream_v4(a.in.c2 + 4 * v), p2 = ld_stream_v4(a.in.p2 + 4 * v);
+        const int4 c1 = ld_stream_v4_hint(a.in.c1 + 4 * v, once), p1 = ld_stream_v4_hint(a.in.p1 + 4 * v, once);
+        const int4 c2 = ld_stream_v4_hint(a.in.c2 + 4 * v, once), p2 = ld_stream_v4_hint(a.in.p2 + 4 * v, once);
         uint32_t mk = 0;
         if (a.in.mark) mk = *reinterpret_cast<const uint32_t*>(a.in.mark + 4 * v);
-        band_apply(a, c1.x, p1.x, c2.x, p2.x, mk & 255, my_oob);
-        band_apply(a, c1.y, p1.y, c2.y, p2.y, (mk >> 8) & 255, my_oob);
-        band_apply(a, c1.z, p1.z, c2.z, p2.z, (mk >> 16) & 255, my_oob);
-        band_apply(a, c1.w, p1.w, c2.w, p2.w, (mk >> 24) & 255, my_oob);
+        band_apply(a, c1.x, p1.x, c2.x, p2.x, mk & 255, my_oob, keep);
+        band_apply(a, c1.y, p1.y, c2.y, p2.y, (mk >> 8) & 255, my_oob, keep);
+        band_apply(a, c1.z, p1.z, c2.z, p2.z, (mk >> 16) & 255, my_oob, keep);
+        band_apply(a, c1.w, p1.w, c2.w, p2.w, (mk >> 24) & 255, my_oob, keep);
     }
     if (blockIdx.x == 0 && threadIdx.x < (int)(a.npairs - nvec * PAIRS_PER_THREAD)) {
         const int64_t i = nvec * PAIRS_PER_THREAD + threadIdx.x;
-        band_apply(a, a.in.c1[i], a.in.p1[i], a.in.c2[i], a.in.p2[i], a.in.mark ? a.in.mark[i] : 0, my_oob);
+        band_apply(a, a.in.c1[i], a.in.p1[i], a.in.c2[i], a.in.p2[i], a.in.mark ? a.in.mark[i] : 0, my_oob, keep);
     }
     if (a.oob) {
         my_oob = (unsigned long long)warp_sum_ll((long long)my_oob);

@@ -70,6 +70,28 @@ __device__ __forceinline__ int4 ld_stream_v4(const int32_t* p) {
     return r;
 }
 
+// L2 eviction policies: streamed inputs should not displace a working set that other warps keep
+// updating in L2 (the band accumulator of the binning kernel)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int4 ld_stream_v4_hint(const int32_t* p, uint64_t policy) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void red_add_s32_hint(int32_t* p, int v, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.s32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void st_stream_v2f64(double* p, double a, double b) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
 }

@@ -64,27 +64,29 @@ ice_csr_stream_kernel(CsrView A, const double* __restrict__ bias, int kd, const 
         double acc0 = 0.0, acc1 = 0.0;
         long long s = 0;
         int nz = 0;
-        long long e = e0 + lane;
-        for (; e + 96 < e1; e += 128) {   // 4 independent coalesced loads per array in flight
-            int c[4], v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { c[u] = __ldg(A.col + e + 32 * u); v[u] = __ldg(A.cnt + e + 32 * u); }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double w = csr_band_weight(c[u], r, kd);
-                if (FILTER) { s += (long long)(w * v[u]); nz += (v[u] != 0) ? (int)w : 0; }
-                else {
-                    const double t = w * (double)v[u] * __ldg(bias + c[u]);
-                    if (u & 1) acc1 += t; else acc0 += t;
-                }
-            }
-        }
-        for (; e < e1; e += 32) {
-            const int c = __ldg(A.col + e), v = __ldg(A.cnt + e);
+        auto one = [&](int c, int v, double& acc) {
             const double w = csr_band_weight(c, r, kd);
             if (FILTER) { s += (long long)(w * v); nz += (v != 0) ? (int)w : 0; }
-            else acc0 += w * (double)v * __ldg(bias + c);
+            else acc = fma(w * (double)v, __ldg(bias + c), acc);
+        };
+        // head: up to 3 entries until the entry index is a multiple of 4 (16-byte aligned vectors)
+        const long long head = min((long long)((4 - (e0 & 3)) & 3), e1 - e0);
+        if (lane < head) one(__ldg(A.col + e0 + lane), __ldg(A.cnt + e0 + lane), acc0);
+        const long long eb = e0 + head;
+        const long long nvec = (e1 - eb) >> 2;
+        long long v = lane;
+        for (; v + 32 < nvec; v += 64) {      // 2 x (col, cnt) 128-bit streaming loads in flight per lane
+            const int4 c0 = ld_stream_v4(A.col + eb + 4 * v), k0 = ld_stream_v4(A.cnt + eb + 4 * v);
+            const int4 c1 = ld_stream_v4(A.col + eb + 4 * (v + 32)), k1 = ld_stream_v4(A.cnt + eb + 4 * (v + 32));
+            one(c0.x, k0.x, acc0); one(c0.y, k0.y, acc1); one(c0.z, k0.z, acc0); one(c0.w, k0.w, acc1);
+            one(c1.x, k1.x, acc0); one(c1.y, k1.y, acc1); one(c1.z, k1.z, acc0); one(c1.w, k1.w, acc1);
         }
+        for (; v < nvec; v += 32) {
+            const int4 c0 = ld_stream_v4(A.col + eb + 4 * v), k0 = ld_stream_v4(A.cnt + eb + 4 * v);
+            one(c0.x, k0.x, acc0); one(c0.y, k0.y, acc1); one(c0.z, k0.z, acc0); one(c0.w, k0.w, acc1);
+        }
+        const long long et = eb + (nvec << 2);   // tail: fewer than 4 entries
+        if (et + lane < e1) one(__ldg(A.col + et + lane), __ldg(A.cnt + et + lane), acc1);
         if (FILTER) {
             s = warp_sum_ll(s);
             nz = warp_sum_i(nz);

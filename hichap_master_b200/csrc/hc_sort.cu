@@ -16,6 +16,10 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys = 32 KB
 constexpr int MAX_PASSES = 8;
+#ifndef HC_SORT_MIN_BLOCKS
+#define HC_SORT_MIN_BLOCKS 4
+#endif
+constexpr int SORT_MIN_BLOCKS = HC_SORT_MIN_BLOCKS;   // 64 registers/thread -> 4 CTAs (32 warps) per SM
 
 constexpr unsigned long long FLAG_AGG = 1ull << 62;
 constexpr unsigned long long FLAG_INC = 2ull << 62;
@@ -67,7 +71,7 @@ struct SortSmem {
     unsigned int tile_id;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS)
 radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
                       int shift, const unsigned long long* __restrict__ digit_base /*[256]*/,
                       unsigned long long* status /*[num_tiles][256]*/, unsigned int* tile_counter) {

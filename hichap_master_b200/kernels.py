@@ -124,11 +124,11 @@ class PinnedPool:
 _RECORD_POOL = PinnedPool()
 
 
-def dense_batch_triu_records(batch: DenseBatch, pool: PinnedPool = None):
+def dense_batch_triu_records(batch: DenseBatch, pool: PinnedPool = None, sync=True):
     """Upper-triangular records of EVERY matrix of the batch in the reference's structured
     layout (matrixBuilding.py:508-524), produced on the device and copied to the host once.
-    Returns a list (one per matrix) of S_DTYPE arrays that are views of one pinned buffer --
-    valid until the next call with the same pool."""
+    Returns (list of S_DTYPE arrays, one per matrix, that are views of one pinned buffer --
+    valid until the next call with the same pool --, bytes copied)."""
     pool = _RECORD_POOL if pool is None else pool
     dev, n = batch.device, batch.nbins
     row_ptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
@@ -143,7 +143,8 @@ def dense_batch_triu_records(batch: DenseBatch, pool: PinnedPool = None):
                                                 ptr(batch.mat_ld), ptr(batch.bin_off), len(batch), n, ptr(row_ptr),
                                                 ptr(dbuf), stream_ptr()), "hc_dense_batch_triu_records")
         host[:24 * total].copy_(dbuf[:24 * total], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if sync:                                  # sync=False: the caller synchronises the stream it issued this on
+            torch.cuda.current_stream().synchronize()
     rec = host[:24 * total].numpy().view(S_DTYPE)
     return [rec[int(bounds[i]):int(bounds[i + 1])] for i in range(len(batch))], 24 * total
 

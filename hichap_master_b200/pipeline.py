@@ -5,8 +5,6 @@ local resolutions: TraditionalMatrixBuilding (:640) then `cooler balance --cis-o
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import torch
 
@@ -16,16 +14,25 @@ from .device import DenseBatch, PairColumns, ptr, require_cuda, stream_ptr
 
 
 class HostPairs:
-    """Columnar pairs in pinned host memory (what a parser hands to the stage)."""
+    """Columnar pairs in pinned host memory (what a parser hands to the stage): chromosome index
+    as uint8 (255 = filtered; fewer bytes over PCIe) and fragment mid-point as int32."""
 
     def __init__(self, c1, p1, c2, p2):
-        def pin(x):
-            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32))
-            t = t.to("cpu", torch.int32).contiguous()
+        def pin(x, dt):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            t = t.to("cpu")
+            if dt == torch.uint8:
+                if int(t.max().item() if t.numel() else 0) >= 255:
+                    raise ValueError("more than 254 chromosomes: use int32 PairColumns")
+                t = torch.where(t < 0, torch.full_like(t, 255), t).to(torch.uint8)
+            else:
+                t = t.to(torch.int32)
+            t = t.contiguous()
             return t if t.is_pinned() else t.pin_memory()
-        self.c1, self.p1, self.c2, self.p2 = (pin(x) for x in (c1, p1, c2, p2))
-        self.n = int(self.c1.numel())
-        self.nbytes = 16 * self.n
+        self.c1, self.c2 = pin(c1, torch.uint8), pin(c2, torch.uint8)
+        self.p1, self.p2 = pin(p1, torch.int32), pin(p2, torch.int32)
+        self.n = int(self.p1.numel())
+        self.nbytes = 10 * self.n
 
 
 class LocalStage:
@@ -35,30 +42,42 @@ class LocalStage:
         self.dev = require_cuda(device)
         self.batch = DenseBatch(sizes, self.dev)
         self.max_pairs = int(max_pairs)
-        self.cols = [torch.empty(max(self.max_pairs, 4), dtype=torch.int32, device=self.dev) for _ in range(4)]
+        n = max(self.max_pairs, 4)
+        self.cols = [torch.empty(n, dtype=torch.int32, device=self.dev) for _ in range(4)]
+        self.chrom8 = [torch.empty(n, dtype=torch.uint8, device=self.dev) for _ in range(2)]
         self.weights_host = torch.empty(self.batch.nbins, dtype=torch.float64).pin_memory()
         self.pool = kernels.PinnedPool()
         self.banded = True      # banded binning (hc_bin_pairs_local_banded)
         self.bin_work = None
+        self.side = torch.cuda.Stream(device=self.dev)
 
     def upload(self, hp: HostPairs) -> PairColumns:
         assert hp.n <= self.max_pairs
-        for d, s in zip(self.cols, (hp.c1, hp.p1, hp.c2, hp.p2)):
-            d[:hp.n].copy_(s, non_blocking=True)
-        return PairColumns(*(d[:hp.n] for d in self.cols), device=self.dev)
+        n = hp.n
+        self.cols[1][:n].copy_(hp.p1, non_blocking=True)
+        self.cols[3][:n].copy_(hp.p2, non_blocking=True)
+        for k, (src, dst) in enumerate(((hp.c1, self.cols[0]), (hp.c2, self.cols[2]))):
+            self.chrom8[k][:n].copy_(src, non_blocking=True)
+            check(lib().hc_widen_u8_i32(ptr(self.chrom8[k]), ptr(dst), n, stream_ptr()), "hc_widen_u8_i32")
+        return PairColumns(*(d[:n] for d in self.cols), device=self.dev)
 
     def run(self, pairs: PairColumns, res: int, records=False, weights_to_host=True, **ice_kw):
-        """zero tiles -> bin -> [extract upper-triangular records] -> filters -> ICE."""
+        """zero tiles -> bin -> [upper-triangular records, copied out on a side stream while ICE
+        runs] -> filters -> ICE."""
         b = self.batch
         b.buf.zero_()
         if self.banded:
             self.bin_work = kernels.bin_pairs_local_banded(pairs, res, b, check_bounds=False, work=self.bin_work)
         else:
             kernels.bin_pairs_local(pairs, res, b, check_bounds=False)
-        recs = None
-        d2h = 0
+        recs, d2h = None, 0
+        main = torch.cuda.current_stream()
         if records:
-            recs, nbytes = kernels.dense_batch_triu_records(b, self.pool)
+            binned = torch.cuda.Event()
+            binned.record(main)
+            self.side.wait_event(binned)
+            with torch.cuda.stream(self.side):
+                recs, nbytes = kernels.dense_batch_triu_records(b, self.pool, sync=False)
             d2h += nbytes
         params = kernels.ice_params(**ice_kw)
         bias = kernels.ice_dense_filters(b, params)
@@ -66,4 +85,6 @@ class LocalStage:
         if weights_to_host:
             self.weights_host.copy_(bias, non_blocking=False)
             d2h += 8 * b.nbins
+        if records:
+            self.side.synchronize()
         return dict(bias=bias, results=results, info=info, records=recs, d2h_bytes=d2h)

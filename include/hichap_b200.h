@@ -77,6 +77,10 @@ int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_
                               const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
                               void* work, void* stream);
 
+/* Chromosome-id columns may cross PCIe as uint8 (255 = filtered chromosome): widen to the int32
+ * columns the binning entry points take (255 -> -1). */
+int hc_widen_u8_i32(const uint8_t* src, int32_t* dst, int64_t n, void* stream);
+
 /* dst[i] += src[i]: replicate merge of dense tiles (matrixBuilding.py:1700-1719). */
 int hc_add_i32(int32_t* dst, const int32_t* src, int64_t n, void* stream);
 
