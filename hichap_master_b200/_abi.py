@@ -75,6 +75,9 @@ SIGNATURES = {
     "hc_ice_csr_work_bytes": (C.c_int64, [_I64, _I32]),
     "hc_ice_csr_balance": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I32, C.POINTER(_I64), C.POINTER(IceParams),
                                      _P, _P, _P, C.POINTER(IceRunInfo), _P, _P]),
+    "hc_ingest_parse": (C.c_int, [C.POINTER(C.c_char_p), _I32, _I32, C.POINTER(C.c_char_p), _I32,
+                                  C.POINTER(C.c_char_p), _I32, _I32, C.POINTER(_I64)]),
+    "hc_ingest_fetch": (C.c_int, [_P, _P, _P, _P, _P]),
     "hc_nccl_available": (C.c_int, []),
     "hc_nccl_unique_id": (C.c_int, [_P]),
     "hc_nccl_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),

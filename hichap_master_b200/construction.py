@@ -31,7 +31,7 @@ from .device import DenseBatch, PairColumns, require_cuda
 from .matrixBuilding import (GenomeWideMatrixCorrection, Get_Chro_Bins_Haplotypes, IntraMatrixToSparseDict,
                              Load_Genome, Sort_Chromosomes, WholeMatrixToSparseDict, _bins_from_genome,
                              _start_table, bin_traditional, chrom_offsets_from_bins, two_step_device)
-from .pairs import read_pairs
+from .pairs import read_pair_files
 
 log = logging.getLogger(__name__)
 
@@ -128,7 +128,7 @@ def TraditionalMatrixConstruction(OutPath, RepPath, genomeSize, wholeRes, localR
         files = [i for i in os.listdir(rep_p) if "_Valid.bed" in i]
         prefix = files[0].split("Valid")[0]
         files = [os.path.join(rep_p, f) for f in files]
-        c1, p1, c2, p2, _ = read_pairs(Merge_beds(files), order, chroms, "valid23")
+        c1, p1, c2, p2, _ = read_pair_files(files, order, chroms, "valid23")   # `cat files` + per-line parse
         whole, local = bin_traditional(PairColumns(c1, p1, c2, p2, device=dev), genome, wholeRes, localRes, dev)
         store = _store_traditional(os.path.join(CoolerPath, prefix + "Multi.npz"), genome, whole, local)
         if balance:
@@ -192,7 +192,7 @@ def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev):
     cols = {}
     for tag in ("Bi_Allelic", "M_M", "P_P", "M_P", "P_M"):
         fs = [f for f in bed_files if (tag + ".bed") in f]
-        c1, p1, c2, p2, mark = read_pairs(Merge_beds(fs), order, chroms, "allelic")
+        c1, p1, c2, p2, mark = read_pair_files(fs, order, chroms, "allelic")
         cols[tag] = PairColumns(c1, p1, c2, p2, mark, dev)
     # traditional matrices: all five classes together (:1081-1094)
     allp = PairColumns(*(torch.cat([getattr(cols[t], a) for t in cols]) for a in ("c1", "p1", "c2", "p2")), device=dev)

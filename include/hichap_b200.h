@@ -281,6 +281,23 @@ int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const double* al
                        const uint8_t* gapflag, int32_t has_gap, const int64_t* rowsum_x,
                        double* out, int64_t ld_out, void* work, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Valid-pair text ingest (host, multithreaded): parses the 23-column
+ * *_Valid.bed (layout 0: chromosomes in columns 1 and 8, fragment mid-points in columns 6 and 13;
+ * matrixBuilding.py:573-586) or the 4/5-column allelic beds (layout 1: c1 p1 c2 p2 [mark];
+ * :822-834, :1131-1141) of several files in order (the reference pipes `cat`, :307-313), with the
+ * reference's `lstrip('chr')` character-set strip and chromosome filter (:360, :577).
+ * chrom_names[i]: stripped name of chromosome index i; filter_names: the `chroms` list ("#" =
+ * numeric labels; nfilter = 0 keeps all).  Dropped lines are omitted.  hc_ingest_parse returns the
+ * number of kept pairs; hc_ingest_fetch (same host thread) copies the columns out and frees them.
+ * Errors: HC_ERR_ARG with hc_last_error() "KeyError: <chrom>" (passes the filter but is not in the
+ * genome table), "ValueError: ..." or "IOError: ...". */
+int hc_ingest_parse(const char* const* h_paths, int32_t npaths, int32_t layout,
+                    const char* const* h_chrom_names, int32_t nchrom,
+                    const char* const* h_filter_names, int32_t nfilter, int32_t nthreads,
+                    int64_t* h_npairs);
+int hc_ingest_fetch(int32_t* h_c1, int32_t* h_p1, int32_t* h_c2, int32_t* h_p2, uint8_t* h_mark);
+
 #ifdef __cplusplus
 }
 #endif

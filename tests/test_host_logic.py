@@ -72,3 +72,67 @@ def test_unknown_chromosome_raises_keyerror(small_genome_file):
     order = ho.sort_chromosomes(genome)
     with pytest.raises(KeyError):
         pairs.read_pairs(io.StringIO("chr7\t1\tchr1\t2\tBoth\n"), order, CHROMS, "allelic")
+
+
+def test_cli_flags_match_reference_matrix_subcommand():
+    """scripts/hichap:392-427: same flags and defaults for `matrix`."""
+    from hichap_master_b200.__main__ import getargs
+    a = getargs(["matrix", "-b", "r1", "r2", "-o", "out", "-N", "-gs", "gs", "-wR", "1000000", "-C"])
+    assert a.bedPath == ["r1", "r2"] and a.NonAllelic and a.wholeRes == [1000000] and a.chroms == []
+    d = getargs(["matrix", "-b", "r1", "-o", "out", "-gs", "gs"])
+    assert d.localRes == [500000, 40000] and d.wholeRes is None and d.chroms == ["#", "X"]
+    assert (d.ImputationRatio, d.ImputationMin, d.ImputationRegion, d.NonAllelic) == (0.9, 2, 10000000, False)
+
+
+# ---- native multithreaded ingest (hc_ingest_parse): CPU-only, no GPU needed -------------------
+@pytest.mark.parametrize("layout", ["valid23", "allelic"])
+@pytest.mark.parametrize("chroms", [["#", "X"], [], ["2", "X"]])
+def test_native_parser_matches_oracle(tmp_path, small_genome_file, layout, chroms):
+    genome = ho.load_genome(small_genome_file, chroms)
+    order = ho.sort_chromosomes(genome)
+    names = [c for c in SMALL_GENOME if c != "M"]
+    big = {c: SMALL_GENOME[c] for c in names}
+    files, lines_all = [], []
+    for k, seed in enumerate((5, 6, 7)):
+        c1, p1, c2, p2 = synth.genome_pairs(big, names, 4000 + k, seed, trans_frac=0.3)
+        if layout == "valid23":
+            lines = list(synth.valid23_lines(names, c1, p1, c2, p2))
+        else:
+            mark = np.random.default_rng(seed).integers(0, 3, size=c1.size)
+            lines = list(synth.allelic_lines(names, c1, p1, c2, p2, mark if k < 2 else None))   # last file: 4 columns
+        if k == 1:
+            lines[10] = lines[10].replace("\t", "  \t ", 3)      # runs of mixed whitespace
+            lines.insert(20, "\n")                               # blank line
+            lines[-1] = lines[-1].rstrip("\n")                   # no trailing newline at EOF
+        f = tmp_path / ("part%d.bed" % k)
+        f.write_text("".join(lines))
+        files.append(str(f)); lines_all.extend(l if l.endswith("\n") else l + "\n" for l in lines)
+    exp = ho.parse_pairs(lines_all, genome, chroms, layout)
+    for nthreads in (1, 3):
+        got = pairs.read_pair_files(files, order, chroms, layout, nthreads=nthreads)
+        for a, b in zip(got[:4], exp[:4]):
+            assert a.dtype == np.int32 and np.array_equal(a, b)
+        if layout == "allelic":
+            assert np.array_equal(got[4], exp[4])
+        else:
+            assert got[4] is None
+
+
+def test_native_parser_errors_and_edge_cases(tmp_path, small_genome_file):
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    order = ho.sort_chromosomes(genome)
+    empty = tmp_path / "empty.bed"; empty.write_text("")
+    got = pairs.read_pair_files([str(empty)], order, CHROMS, "allelic")
+    assert got[0].size == 0 and got[4].size == 0
+    assert pairs.read_pair_files([], order, CHROMS, "valid23")[0].size == 0
+    bad = tmp_path / "bad.bed"; bad.write_text("chr7\t1\tchr1\t2\tBoth\n")      # passes '#' filter, not in genome
+    with pytest.raises(KeyError):
+        pairs.read_pair_files([str(bad)], order, CHROMS, "allelic")
+    ok = tmp_path / "ok.bed"; ok.write_text("chr7\t1\tchrY\t2\tBoth\nchrchr1\t5\trch2\t9\tR1\n")  # filtered mate wins; set-strip
+    got = pairs.read_pair_files([str(ok)], order, CHROMS, "allelic")
+    assert list(got[0]) == [0] and list(got[2]) == [1] and list(got[4]) == [1]
+    junk = tmp_path / "junk.bed"; junk.write_text("chr1\tx\tchr1\t2\tBoth\n")
+    with pytest.raises(ValueError):
+        pairs.read_pair_files([str(junk)], order, CHROMS, "allelic")
+    with pytest.raises(IOError):
+        pairs.read_pair_files([str(tmp_path / "missing.bed")], order, CHROMS, "allelic")
