@@ -126,7 +126,8 @@ struct IceDenseArgs {
     const int32_t* mats; const int64_t* mat_off; const int32_t* mat_n; const int32_t* mat_ld;
     const int64_t* pad_off;     // start of each problem in the padded (ld-strided, 128 B aligned) vectors
     const int32_t* item_prob; const int32_t* item_row0; const int32_t* item_nrows;   // work items (~equal bytes)
-    unsigned int nitems; unsigned int* queue;   // global work queue: warps draw items until it runs dry
+    const unsigned int* nitems; unsigned int* queue;   // global work queue: warps draw items until it runs dry
+    int32_t* iter;              // iteration counter, advanced on the device (the loop is replayed as a CUDA graph)
     double* bias;               // padded layout; updated in place by the update kernel
     double* marg;               // padded layout; fresh marginals of this iteration
     hc_ice_result* results; int32_t* done; int32_t* n_done;
@@ -162,10 +163,14 @@ __global__ void __launch_bounds__(256, MINB)
 ice_dense_stream_kernel(IceDenseArgs A) {
     const int lane = threadIdx.x & 31;
     const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
+    const unsigned nitems = *A.nitems;
     unsigned item = 0;
-    if (lane == 0) item = atomicAdd(A.queue, 1u);
+    if (lane == 0) {
+        item = atomicAdd(A.queue, 1u);
+        if (item == 0) atomicAdd(A.iter, 1);       // exactly one warp per launch draws index 0: it opens iteration k
+    }
     item = __shfl_sync(0xffffffffu, item, 0);
-    while (item < A.nitems) {
+    while (item < nitems) {
         unsigned next = 0;
         if (lane == 0) next = atomicAdd(A.queue, 1u);
         const int p = A.item_prob[item];
@@ -217,13 +222,14 @@ ice_dense_stream_kernel(IceDenseArgs A) {
 // Vector half of an iteration (grid = one CTA per chromosome): mean / variance of the fresh
 // marginals over the non-zero bins, bias update b /= marg/mean (in place), convergence test,
 // scale / iteration bookkeeping -- all on the device.
-__global__ void __launch_bounds__(256)
-ice_dense_update_kernel(IceDenseArgs A, int k) {
+__global__ void __launch_bounds__(1024)
+ice_dense_update_kernel(IceDenseArgs A) {
     __shared__ double red[32];
     __shared__ long long redll[32];
     const int p = blockIdx.x;
+    const int k = *A.iter;                                // opened by this iteration's stream kernel
     if (p == 0 && threadIdx.x == 0) *A.queue = 0;         // re-arm the work queue for the next iteration
-    if (A.done[p]) return;
+    if (A.done[p] || k > A.max_iters) return;
     const int n = A.mat_n[p];
     if (n == 0) return;
     const int64_t lo = A.pad_off[p];
@@ -345,7 +351,6 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
                                     hc_ice_result* results, hc_ice_run_info* h_info, void* stream) {
     HC_REQUIRE(nprob > 0 && h_mat_n != nullptr && P != nullptr, "nprob>0, h_mat_n, params");
     HC_REQUIRE(P->max_iters >= 1 && P->ignore_diags >= 0, "max_iters>=1, ignore_diags>=0");
-    cudaStream_t s = (cudaStream_t)stream;
     int64_t nbins = 0;
     for (int p = 0; p < nprob; ++p) {
         HC_REQUIRE(h_mat_n[p] >= 0, "matrix side");
@@ -353,6 +358,22 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     }
     if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; }
     if (nbins == 0) return HC_OK;
+    // The iteration loop is replayed as a CUDA graph, which cannot be captured on the legacy default
+    // stream: run on a private stream ordered after the caller's stream (the call synchronises
+    // before returning, so the caller's later work is ordered after it).
+    static thread_local cudaStream_t private_stream[64] = {nullptr};
+    int dev = 0;
+    HC_CUDA(cudaGetDevice(&dev));
+    HC_REQUIRE(dev >= 0 && dev < 64, "device index");
+    if (!private_stream[dev]) HC_CUDA(cudaStreamCreateWithFlags(&private_stream[dev], cudaStreamNonBlocking));
+    cudaStream_t s = private_stream[dev];
+    {
+        cudaEvent_t e_in;
+        HC_CUDA(cudaEventCreateWithFlags(&e_in, cudaEventDisableTiming));
+        HC_CUDA(cudaEventRecord(e_in, (cudaStream_t)stream));
+        HC_CUDA(cudaStreamWaitEvent(s, e_in, 0));
+        cudaEventDestroy(e_in);
+    }
 
     int vi = 0;
     if (const char* e = getenv("HC_ICE_VARIANT")) vi = atoi(e);
@@ -409,27 +430,30 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     HC_CUDA(cudaMemcpyAsync(d_pad, h_pad.data(), (nprob + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     ice_pad_bias_kernel<<<(unsigned)((nbins + 255) / 256), 256, 0, s>>>(bin_off, d_pad, nprob, bias, biasp);
     HC_LAUNCH_CHECK();
-    int32_t* d_tab = nullptr;    // 3 item tables | done[nprob] | n_done | queue
-    const size_t tab_ints = 3 * max_items + (size_t)nprob + 2;
+    int32_t* d_tab = nullptr;    // 3 item tables | done[nprob] | n_done | queue | iter | nitems
+    const size_t tab_ints = 3 * max_items + (size_t)nprob + 4;
     HC_CUDA(cudaMallocAsync((void**)&d_tab, tab_ints * sizeof(int32_t), s));
     auto upload_items = [&]() -> cudaError_t {
         const size_t n = item_prob.size();
-        cudaError_t e = cudaMemcpyAsync(d_tab, item_prob.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        const int32_t n32 = (int32_t)n;
+        cudaError_t e = cudaMemcpyAsync(d_tab + 3 * max_items + nprob + 3, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, item_prob.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab + max_items, item_row0.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab + 2 * max_items, item_nrows.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the host vectors may be rebuilt afterwards
         return e;
     };
+    HC_CUDA(cudaMemsetAsync(d_tab + 3 * max_items, 0, ((size_t)nprob + 3) * sizeof(int32_t), s));
     HC_CUDA(upload_items());
-    HC_CUDA(cudaMemsetAsync(d_tab + 3 * max_items, 0, ((size_t)nprob + 2) * sizeof(int32_t), s));
 
     IceDenseArgs A;
     A.mats = mats; A.mat_off = mat_off; A.mat_n = mat_n; A.mat_ld = mat_ld; A.pad_off = d_pad;
     A.item_prob = d_tab; A.item_row0 = d_tab + max_items; A.item_nrows = d_tab + 2 * max_items;
-    A.nitems = (unsigned)item_prob.size();
     A.done = d_tab + 3 * max_items;
     A.n_done = A.done + nprob;
     A.queue = reinterpret_cast<unsigned int*>(A.n_done + 1);
+    A.iter = A.n_done + 2;
+    A.nitems = reinterpret_cast<const unsigned int*>(A.n_done + 3);
     A.bias = biasp; A.marg = marg; A.results = results;
     A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters; A.nprob = nprob;
 
@@ -448,28 +472,50 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     const int poll = P->poll_every > 0 ? P->poll_every : 8;
     int launches = 0, h_ndone = 0, seen_done = 0;
     int rc = HC_OK;
+    // `poll` iterations (stream + update kernel each) captured once and replayed: the iteration index,
+    // the work-list length and every convergence decision live in device memory, so the graph is static
+    cudaGraphExec_t gexec = nullptr;
+    bool use_graph = true;
+    if (const char* e = getenv("HC_ICE_GRAPH")) use_graph = atoi(e) != 0;
+    if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            for (int i = 0; i < poll; ++i) {
+                V.fn<<<grid, 256, 0, s>>>(A);
+                ice_dense_update_kernel<<<nprob, 1024, 0, s>>>(A);
+            }
+            e = cudaStreamEndCapture(s, &graph);
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { gexec = nullptr; (void)cudaGetLastError(); }   // plain launches below
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the iteration loop, for the roofline
     if (h_info) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, s); }
-    for (int k = 1; k <= P->max_iters; ++k) {
-        V.fn<<<grid, 256, 0, s>>>(A);
-        ice_dense_update_kernel<<<nprob, 256, 0, s>>>(A, k);
-        hc_count_launch(2);
-        launches += 2;
-        if (k % poll == 0 || k == P->max_iters) {
-            cudaError_t e = cudaMemcpyAsync(&h_ndone, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e == cudaSuccess && h_ndone >= nonempty) break;
-            if (e == cudaSuccess && h_ndone != seen_done) {
-                // drop the converged chromosomes from the work list (their items would only be skipped)
-                seen_done = h_ndone;
-                e = cudaMemcpyAsync(h_done.data(), A.done, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-                if (e == cudaSuccess) { build_items(); e = upload_items(); A.nitems = (unsigned)item_prob.size(); }
-            }
-            if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
+    for (int k0 = 0; k0 < P->max_iters; k0 += poll) {
+        cudaError_t e = cudaSuccess;
+        if (gexec) e = cudaGraphLaunch(gexec, s);
+        else for (int i = 0; i < poll; ++i) {
+            V.fn<<<grid, 256, 0, s>>>(A);
+            ice_dense_update_kernel<<<nprob, 1024, 0, s>>>(A);
         }
+        hc_count_launch(2 * poll);
+        launches += 2 * poll;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_ndone, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess && h_ndone >= nonempty) break;
+        if (e == cudaSuccess && h_ndone != seen_done) {
+            // drop the converged chromosomes from the work list (their items would only be skipped)
+            seen_done = h_ndone;
+            e = cudaMemcpyAsync(h_done.data(), A.done, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess) { build_items(); e = upload_items(); }
+        }
+        if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
     }
     if (h_info && ev0) cudaEventRecord(ev1, s);
+    if (gexec) cudaGraphExecDestroy(gexec);
     if (rc == HC_OK) {
         const int64_t blocks = (nbins + 255) / 256;
         ice_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin_off, d_pad, nprob, results, P->rescale_marginals, biasp, bias);

@@ -66,7 +66,9 @@ def main():
         msg = ["world=%d iters=%d (oracle %d) max_rel_err=%.2e identical_across_ranks=%s nnz/rank=%s imbalance=%.3f "
                "launches=%d loop_ms=%.2f cuts=%s" % (world, st["iters"], rst["iters"], err, same, sizes, bal,
                                                      st["launches"], st["loop_ms"], cuts)]
-        ok = ok and bal < 1.25
+        # rows are the sharding granularity: a rank may exceed the mean by at most one (dense) row
+        rows_nnz = np.bincount(np.concatenate([key // total, key % total]), minlength=total)
+        ok = ok and max(sizes) <= sum(sizes) / world + 2 * rows_nnz.max()
         print("DIST_CHECK", "OK" if ok else "FAIL", *msg)
     kernels.nccl_comm_destroy(comm)
     dist.destroy_process_group()
