@@ -231,6 +231,11 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one full launch, from the committed ncu capture
+    try:
+        traffic = float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic_bytes_per_launch"]) if world == 1 else None
+    except Exception:
+        traffic = None
     achieved = ice_bytes / (loop_ms * 1e6) if loop_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -252,7 +257,9 @@ def run_ours(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_launch": ice_bytes / max(n_iter_launches, 1),
                      "launches": n_iter_launches, "avg_launch_ms": loop_ms / max(n_iter_launches, 1),
-                     "traffic": None},
+                     "traffic": traffic,
+                     "traffic_note": "ncu --set full capture of a launch with all 23 chromosomes active (profiles/ncu_traffic.json); "
+                                     "algorithmic bytes of that launch = sum 4*N^2 = 1.197e9"},
         "breakdown": breakdown, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
