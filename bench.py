@@ -259,7 +259,7 @@ def run_ours(args):
                      "launches": n_iter_launches, "avg_launch_ms": loop_ms / max(n_iter_launches, 1),
                      "traffic": traffic,
                      "traffic_note": "ncu --set full capture of a launch with all 23 chromosomes active (profiles/ncu_traffic.json); "
-                                     "algorithmic bytes of that launch = sum 4*N^2 = 1.197e9"},
+                                     "algorithmic bytes of that launch = sum 4*N^2 = 1.183e9 (1.205e9 with the 128-column row padding)"},
         "breakdown": breakdown, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
