@@ -132,6 +132,7 @@ struct IceDenseArgs {
     double* marg;               // padded layout; fresh marginals of this iteration
     hc_ice_result* results; int32_t* done; int32_t* n_done;
     double tol; int kd; int max_iters; int nprob;
+    unsigned int queue_start;   // number of warps of the stream kernel: items below it are pre-assigned
 };
 
 // one column chunk (128 columns, 4 per lane) of RG rows: acc[q] += sum_j w * A[rq][j] * b[j]
@@ -164,12 +165,10 @@ ice_dense_stream_kernel(IceDenseArgs A) {
     const int lane = threadIdx.x & 31;
     const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
     const unsigned nitems = *A.nitems;
-    unsigned item = 0;
-    if (lane == 0) {
-        item = atomicAdd(A.queue, 1u);
-        if (item == 0) atomicAdd(A.iter, 1);       // exactly one warp per launch draws index 0: it opens iteration k
-    }
-    item = __shfl_sync(0xffffffffu, item, 0);
+    // first item = global warp index (no atomic: 4736 simultaneous draws on one address would serialise
+    // the start of every launch); the queue counter is re-armed to the warp count by the update kernel
+    unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.iter, 1);       // opens iteration k
     while (item < nitems) {
         unsigned next = 0;
         if (lane == 0) next = atomicAdd(A.queue, 1u);
@@ -228,7 +227,7 @@ ice_dense_update_kernel(IceDenseArgs A) {
     __shared__ long long redll[32];
     const int p = blockIdx.x;
     const int k = *A.iter;                                // opened by this iteration's stream kernel
-    if (p == 0 && threadIdx.x == 0) *A.queue = 0;         // re-arm the work queue for the next iteration
+    if (p == 0 && threadIdx.x == 0) *A.queue = A.queue_start;   // re-arm the work queue for the next iteration
     if (A.done[p] || k > A.max_iters) return;
     const int n = A.mat_n[p];
     if (n == 0) return;
@@ -375,9 +374,17 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         cudaEventDestroy(e_in);
     }
 
-    int vi = 0;
+    // variant: 4 rows per warp step is the fastest per byte, but a warp item is at least RG rows; when the
+    // batch is small (one large chromosome per GPU in the 8-way sharded run) fewer rows per item keep
+    // every resident warp busy.  HC_ICE_VARIANT overrides (tuning).
+    int vi = -1;
     if (const char* e = getenv("HC_ICE_VARIANT")) vi = atoi(e);
-    if (vi < 0 || vi >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) vi = 0;
+    if (vi < 0 || vi >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) {
+        int64_t rows = 0;
+        for (int p = 0; p < nprob; ++p) rows += h_mat_n[p];
+        const int64_t warps = (int64_t)hc_num_sms() * 4 * 8;
+        vi = rows / 4 >= warps + warps / 4 ? 0 : (rows / 2 >= warps + warps / 4 ? 2 : 5);   // <4,2,4> | <2,2,4> | <1,4,4>
+    }
     const StreamVariant V = kVariants[vi];
     int item_kb = 32;   // bytes of matrix per work item: small enough that the last item is a short tail
     if (const char* e = getenv("HC_ICE_ITEM_KB")) item_kb = std::max(1, atoi(e));
@@ -445,6 +452,9 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     };
     HC_CUDA(cudaMemsetAsync(d_tab + 3 * max_items, 0, ((size_t)nprob + 3) * sizeof(int32_t), s));
     HC_CUDA(upload_items());
+    const int grid = hc_num_sms() * V.minb;    // persistent: every resident slot filled exactly once
+    const unsigned int queue_start = (unsigned)grid * 8u;
+    HC_CUDA(cudaMemcpyAsync(d_tab + 3 * max_items + nprob + 1, &queue_start, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
 
     IceDenseArgs A;
     A.mats = mats; A.mat_off = mat_off; A.mat_n = mat_n; A.mat_ld = mat_ld; A.pad_off = d_pad;
@@ -455,7 +465,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     A.iter = A.n_done + 2;
     A.nitems = reinterpret_cast<const unsigned int*>(A.n_done + 3);
     A.bias = biasp; A.marg = marg; A.results = results;
-    A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters; A.nprob = nprob;
+    A.tol = P->tol; A.kd = P->ignore_diags; A.max_iters = P->max_iters; A.nprob = nprob; A.queue_start = queue_start;
 
     int nonempty = 0;
     for (int p = 0; p < nprob; ++p) nonempty += h_mat_n[p] > 0;
@@ -467,8 +477,6 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     }
     // the bias vector is the only data that should live in L1: no shared-memory carve-out
     cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    const int grid = hc_num_sms() * V.minb;    // persistent: every resident slot filled exactly once
-
     const int poll = P->poll_every > 0 ? P->poll_every : 8;
     int launches = 0, h_ndone = 0, seen_done = 0;
     int rc = HC_OK;
