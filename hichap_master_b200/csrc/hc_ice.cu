@@ -165,10 +165,14 @@ ice_dense_stream_kernel(IceDenseArgs A) {
     const int lane = threadIdx.x & 31;
     const int kd = A.kd, kspan = kd > 0 ? kd - 1 : 0;
     const unsigned nitems = *A.nitems;
-    // first item = global warp index (no atomic: 4736 simultaneous draws on one address would serialise
+    // the first item of a warp is its global index (4736 simultaneous draws on one address would serialise
     // the start of every launch); the queue counter is re-armed to the warp count by the update kernel
-    unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.iter, 1);       // opens iteration k
+    unsigned item = 0;
+    if (lane == 0) {
+        item = (blockIdx.x * 256u + threadIdx.x) >> 5;
+        if (item == 0) atomicAdd(A.iter, 1);       // exactly one warp per launch owns index 0: it opens iteration k
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
     while (item < nitems) {
         unsigned next = 0;
         if (lane == 0) next = atomicAdd(A.queue, 1u);

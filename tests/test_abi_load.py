@@ -40,3 +40,16 @@ def test_struct_layout_matches_header():
     from hichap_master_b200 import _abi
     assert ctypes.sizeof(_abi.IceParams) == 40
     assert ctypes.sizeof(_abi.IceResult) == 24
+
+
+def test_default_ice_stream_variant_does_not_spill():
+    """The <4,2,4> ICE stream kernel sits exactly at the 64-register budget of 4 CTAs/SM; a spill
+    costs ~20 % of its bandwidth (profiles/README.md), so the build log is checked."""
+    log = os.path.join(ROOT, "hichap_master_b200", "csrc", "hc_ice.o.ptxas.log")
+    if not os.path.isfile(log):
+        import pytest
+        pytest.skip("no ptxas log (library built elsewhere)")
+    text = open(log).read()
+    m = re.search(r"ice_dense_stream_kernelILi4ELi2ELi4E.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", text, flags=re.S)
+    assert m, "default variant not found in the ptxas log"
+    assert (int(m.group(2)), int(m.group(3))) == (0, 0), m.group(0)[-120:]
