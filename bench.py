@@ -370,7 +370,7 @@ def run_c4(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    res = 10000
+    res = 10000 if args.config == "C4" else 5000
     genome, order = c2_genome()
     bins, total = mb._bins_from_genome(genome, res, [(c, c) for c in order])
     start = mb._start_table(bins, order, dev)
@@ -414,8 +414,9 @@ def run_c4(args):
         Z = (out["nnz_stored"] + total) / 2
         per_iter = out["loop_s"] / max(out["iters"], 1)
         print(json.dumps({
-            "config": {"workload": "C4: hg19 genome-wide 10 kb (%d bins), %d synthetic pairs (75%% cis / 25%% trans), "
-                                   "row-block sharded CSR over %d GPU(s), one NCCL allreduce per ICE iteration" % (total, args.pairs, world)},
+            "config": {"workload": "%s: hg19 genome-wide %d kb (%d bins), %d synthetic pairs (75%% cis / 25%% trans), "
+                                   "row-block sharded CSR over %d GPU(s), one NCCL allreduce per ICE iteration"
+                                   % (args.config, res // 1000, total, args.pairs, world)},
             "n_gpus": world, "binning_to_csr_s": out["build_s"], "ice_time_to_convergence_s": out["ice_s"],
             "ice_loop_s": out["loop_s"], "ice_iters": out["iters"], "converged": out["converged"],
             "nnz_upper": Z, "nnz_stored_total": out["nnz_stored"], "nnz_imbalance": out["nnz_max_rank"] * world / out["nnz_stored"],
@@ -436,11 +437,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="kernel tuning runs only: no e2e leg (line is not a bench result)")
-    ap.add_argument("--config", default="C2", choices=["C2", "C4"], help="C2 = the driver's headline workload")
+    ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"], help="C2 = the driver's headline workload")
     args = ap.parse_args()
-    if args.config == "C4":
+    if args.config in ("C4", "C5"):
         if args.pairs == 400_000_000:
-            args.pairs = 1_000_000_000
+            args.pairs = 1_000_000_000 if args.config == "C4" else 2_000_000_000
         return run_c4(args)
     if args.impl == "reference":
         args.steps = min(args.steps, 3)

@@ -112,7 +112,10 @@ ice_csr_stream_kernel(CsrView A, const double* __restrict__ bias, int kd, const 
 // asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier: the TMA engine
 // moves the 64 KB while the warps fetch their row pointers), and serves in-window columns from
 // shared memory; only the far / trans columns still gather 32-byte sectors from L2.
-constexpr int WIN = 8192;            // doubles: 64 KB window
+#ifndef HC_CSR_WIN
+#define HC_CSR_WIN 2048
+#endif
+constexpr int WIN = HC_CSR_WIN;      // doubles: 16 KB window (20 Mb of 10 kb bins), 8 CTAs per SM
 constexpr int ROWS_PER_CTA = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -357,7 +360,7 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
     // contacts outside any window and the 64 KB windows cut occupancy to 24 warps/SM; opt-in only.
     bool use_window = false;
     if (const char* e = getenv("HC_CSR_WINDOW")) use_window = atoi(e) != 0;
-    const int window_grid = hc_num_sms() * 3;     // 3 x 64 KB windows per SM
+    const int window_grid = hc_num_sms() * 8;     // 8 x 16 KB windows per SM
     if (use_window)
         HC_CUDA(cudaFuncSetAttribute(ice_csr_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WIN * sizeof(double))));
     HC_CUDA(cudaMemsetAsync(marg, 0, sizeof(double) * 2 * nbins, s));
