@@ -428,6 +428,64 @@ def run_c4(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """--config C3 (BASELINE.json configs[2]): allelic maternal/paternal matrices at 40 kb with the
+    two-step (ICE of the traditional matrices + SNP-density / coverage) correction.  Single GPU;
+    prints one JSON line with the stage breakdown."""
+    import torch
+    from hichap_master_b200 import _abi, kernels, matrixBuilding as mb, synth
+    from hichap_master_b200.construction import _sub_batch
+    from hichap_master_b200.device import DenseBatch, PairColumns
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    genome, order = c2_genome()
+    nchrom = len(order)
+    pairs_n = args.pairs if args.pairs != 400_000_000 else 100_000_000
+    c1, p1, c2, p2 = synth.genome_pairs_torch(genome, order, pairs_n, 3, dev, trans_frac=0.0)
+    g = torch.Generator(device=dev); g.manual_seed(33)
+    cls = torch.rand(pairs_n, generator=g, device=dev)          # Bi 86 %, M_M 6 %, P_P 6 %, M_P 1 %, P_M 1 %
+    mark = torch.multinomial(torch.tensor([0.30, 0.35, 0.35], device=dev), pairs_n, replacement=True, generator=g).to(torch.uint8)
+    allp = PairColumns(c1, p1, c2, p2, device=dev)
+    hap = []
+    for lo, hi in ((0.86, 0.92), (0.92, 0.98)):
+        sel = (cls >= lo) & (cls < hi)
+        hap.append(PairColumns(c1[sel], p1[sel], c2[sel], p2[sel], mark[sel], device=dev))
+    sizes = [genome[c] // RES + 1 for c in order]
+    T = DenseBatch(sizes, dev)
+    H = DenseBatch(sizes + sizes, dev)
+
+    def ev(fn):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = fn(); b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b), out
+
+    def bin_all():
+        T.buf.zero_(); H.buf.zero_()
+        kernels.bin_pairs_local_banded(allp, RES, T, check_bounds=False)
+        for k in range(2):
+            v = _sub_batch(H, k * nchrom, nchrom)
+            kernels.bin_pairs_local(hap[k], RES, v, _abi.HC_BIN_SYM_BOTH, check_bounds=False)
+            kernels.bin_pairs_local(hap[k], RES, v, _abi.HC_BIN_ONESIDED, check_bounds=False)
+
+    def correct_all():
+        return kernels.twostep_batch(T, H)
+
+    res_t = {}
+    for rep in range(2):
+        res_t["binning_ms"], _ = ev(bin_all)
+        res_t["ice_traditional_ms"], (w, st) = ev(lambda: kernels.ice_balance_dense(T, None, ignore_diags=1))
+        res_t["two_step_ms"], outs = ev(correct_all)
+    sq = float(sum(n * n for n in sizes))
+    print(json.dumps({
+        "config": {"workload": "C3: hg19 chr1-22,X allelic matrices at 40 kb, %d synthetic pairs (86%% bi-allelic, 6%% M_M, 6%% P_P; "
+                               "Both/R1/R2 = 30/35/35%%), ICE of the traditional matrices + two-step correction of M and P" % pairs_n},
+        "n_gpus": 1, **res_t, "total_ms": sum(res_t.values()), "ice_iters_max": int(max(st["iters"])),
+        "two_step_algorithmic_GBps": 52.0 * sq / (res_t["two_step_ms"] * 1e6),
+        "gap_rows_total": int(sum(g.size for g in outs[1]))}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -437,8 +495,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="kernel tuning runs only: no e2e leg (line is not a bench result)")
-    ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"], help="C2 = the driver's headline workload")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"], help="C2 = the driver's headline workload")
     args = ap.parse_args()
+    if args.config == "C3":
+        return run_c3(args)
     if args.config in ("C4", "C5"):
         if args.pairs == 400_000_000:
             args.pairs = 1_000_000_000 if args.config == "C4" else 2_000_000_000

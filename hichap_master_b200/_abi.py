@@ -63,6 +63,10 @@ SIGNATURES = {
     "hc_twostep_alpha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_twostep_work_bytes": (C.c_int64, [_I32]),
     "hc_twostep_correct": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P]),
+    "hc_twostep_batch_work_bytes": (C.c_int64, [_I64, _I64, _I32]),
+    "hc_twostep_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(_I32), C.POINTER(_I64),
+                                   C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64), _P, C.POINTER(_I64), _P, _P, _P, _P,
+                                   _P, _P]),
     "hc_pairs_to_keys": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hc_sort_work_bytes": (C.c_int64, [_I64]),
     "hc_sort_keys_u64": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, C.POINTER(_I32), _P]),

@@ -283,10 +283,9 @@ def _haplotype_outputs(OutPath, prefix, genome, data: HaplotypeData, wholeRes, l
         imp.add(res, WholeMatrixToSparseDict_float(hb, nor_whole[res]), hb)
     for res in localRes:
         T, H = data.tra_local[res], data.imp_local[res]
-        nor, gaps = {}, {}
-        for i, c in enumerate(order):                                                     # :1031-1039
-            a, b, ga, gb = two_step_device(T, i, H, i, H, nchrom + i)
-            nor["M" + c], nor["P" + c], gaps["M" + c], gaps["P" + c] = a, b, ga, gb
+        mats, gl = kernels.twostep_batch(T, H)                                            # :1031-1039, one call
+        nor = {("M" if k < nchrom else "P") + order[k % nchrom]: mats[k] for k in range(2 * nchrom)}
+        gaps = {("M" if k < nchrom else "P") + order[k % nchrom]: gl[k] for k in range(2 * nchrom)}
         nor_local[res], gap_local[str(res)] = nor, gaps
         imp.add(res, IntraMatrixToSparseDict(nor))
     np.savez(os.path.join(OutPath, prefix + "Imputated_Gap.npz"), **gap_local)            # :1616-1617

@@ -56,6 +56,8 @@ struct AlphaArgs {
     double* alpha; uint8_t* gf_a; uint8_t* gf_b; int32_t* gi_a; int32_t* gi_b; int32_t* ngap;
     double* work;
     double q25, q20;
+    // batched path (grid = nchrom): per-chromosome offsets into the concatenated vectors; NULL = single problem
+    const int64_t* t_bin_off; const int64_t* h_bin_off; int nchrom;
 };
 
 __device__ void gap_rows(const int32_t* nnz, int n, int ncols, int gap_mode, double q25, double* cov,
@@ -106,6 +108,17 @@ __device__ void compact_flags(const uint8_t* gf, int n, int32_t* idx, int32_t* c
 
 __global__ void __launch_bounds__(1024) twostep_alpha_kernel(AlphaArgs a) {
     __shared__ HcSelectSmem sm;
+    if (a.t_bin_off) {          // batched: chromosome c; M matrix c and P matrix nchrom + c of the haplotype batch
+        const int c = blockIdx.x;
+        const int64_t t0 = a.t_bin_off[c], m0 = a.h_bin_off[c], p0 = a.h_bin_off[a.nchrom + c];
+        a.n = (int)(a.t_bin_off[c + 1] - t0);
+        a.ncols = a.n;
+        a.rs_t += t0; a.rs_m += m0; a.rs_p += p0; a.nnz_a += m0; a.nnz_b += p0;
+        a.alpha += t0; a.gf_a += m0; a.gf_b += p0; a.gi_a += m0; a.gi_b += p0;
+        a.ngap += 2 * c;
+        a.work += 2 * t0;
+        if (a.n == 0) return;
+    }
     const int n = a.n;
     double* cov_a = a.work;
     double* cov_b = a.work + n;
@@ -155,6 +168,7 @@ enum { PASS_ROWSUM = 0, PASS_TOTAL = 1, PASS_WRITE = 2 };
 struct SymArgs {
     const int32_t* X; int64_t ld; int n; int nT;
     const double* alpha; const uint8_t* gapflag; int has_gap;
+    const int32_t* ngap_dev;   // batched path: has_gap = (*ngap_dev > 0), decided on the device (no host round trip)
     double* ra;           // [nT*T] 1 / alpha_i (0 beyond n)
     double* partial;      // [nT][nT*T] per-tile partial row sums of Sym
     double* rs;           // [nT*T] 1 / s_i  (s = rowsum^(2/3), 0 -> 1)
@@ -196,6 +210,7 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
     __shared__ double colred[8][T];
     __shared__ double red[32];
 
+    if (a.ngap_dev) a.has_gap = *a.ngap_dev > 0;
     int I, J;
     tile_index(blockIdx.x, a.nT, &I, &J);
     const int r0 = I * T, c0 = J * T;
@@ -326,6 +341,31 @@ vc_rescale_factor_kernel(const double* __restrict__ cta_partial, int npairs, con
     }
 }
 
+// row sums + non-zero counts of every matrix of a batch (one warp per global row)
+__global__ void __launch_bounds__(256)
+rowstats_batch_kernel(const int32_t* __restrict__ mats, const int64_t* __restrict__ mat_off, const int32_t* __restrict__ mat_n,
+                      const int32_t* __restrict__ mat_ld, const int64_t* __restrict__ bin_off, int nprob,
+                      int64_t* __restrict__ rowsum, int32_t* __restrict__ rownnz) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= bin_off[nprob]) return;
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bin_off[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int p = lo, r = (int)(g - bin_off[p]);
+    const int32_t* row = mats + mat_off[p] + (int64_t)r * mat_ld[p];
+    const int nvec = mat_ld[p] >> 2;            // padding columns are zero
+    long long s = 0;
+    int c = 0;
+    for (int v = lane; v < nvec; v += 32) {
+        const int4 a = ld_stream_v4(row + 4 * v);
+        s += (long long)a.x + a.y + a.z + a.w;
+        c += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+    }
+    s = warp_sum_ll(s);
+    c = warp_sum_i(c);
+    if (lane == 0) { rowsum[g] = s; if (rownnz) rownnz[g] = c; }
+}
+
 struct TwoStepWork { double* partial; double* rs; double* ra; double* cta_partial; double* scalars; };
 
 TwoStepWork carve(void* work, int n) {
@@ -365,6 +405,7 @@ extern "C" int hc_twostep_alpha(const int64_t* rowsum_t, const int64_t* rowsum_m
     a.n = n; a.ncols = ncols; a.gap_mode = gap_mode;
     a.alpha = alpha; a.gf_a = gapflag_a; a.gf_b = gapflag_b; a.gi_a = gapidx_a; a.gi_b = gapidx_b; a.ngap = ngap;
     a.work = work;
+    a.t_bin_off = nullptr; a.h_bin_off = nullptr; a.nchrom = 0;
     a.q25 = 25.0 / 100.0;  // np.percentile divides q by 100 first
     a.q20 = 20.0 / 100.0;
     twostep_alpha_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
@@ -391,6 +432,7 @@ extern "C" int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const
     TwoStepWork w = carve(work, n);
     SymArgs a;
     a.X = X; a.ld = ld; a.n = n; a.nT = nT; a.alpha = alpha; a.gapflag = gapflag; a.has_gap = has_gap ? 1 : 0;
+    a.ngap_dev = nullptr;
     a.partial = w.partial; a.rs = w.rs; a.ra = w.ra; a.cta_partial = w.cta_partial; a.scalars = w.scalars;
     a.out = out; a.ld_out = ld_out;
     const size_t smem_tiles = (size_t)(T * T + T * LDB) * sizeof(int32_t);
@@ -408,5 +450,75 @@ extern "C" int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const
     HC_LAUNCH_CHECK();
     sym_pass_kernel<PASS_WRITE><<<npairs, TS_THREADS, smem_write, s>>>(a);
     HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+
+// ---- whole-batch driver: IntraChromMatrixCorrection (matrixBuilding.py:1026-1041) in one call -----
+// T: nchrom traditional matrices; H: 2*nchrom haplotype matrices (all maternal, then all paternal),
+// same sides.  Everything is enqueued on `stream` with no host round trip: the gap decisions
+// (`has_gap`) are read by the tile kernels from the device counters.  Outputs: out (fp64, matrix k of H
+// at h_out_off[k], row-major n x n), alpha (per T bin), gapflag / gapidx (per H bin), ngap[2*nchrom]
+// ordered (M_c, P_c) per chromosome.
+extern "C" int64_t hc_twostep_batch_work_bytes(int64_t t_nbins, int64_t h_nbins, int32_t max_n) {
+    return (int64_t)sizeof(int64_t) * (t_nbins + h_nbins) + (int64_t)sizeof(int32_t) * h_nbins + (int64_t)sizeof(double) * 2 * t_nbins +
+           hc_twostep_work_bytes(max_n) + 256;
+}
+
+extern "C" int hc_twostep_batch(const int32_t* tmats, const int64_t* t_off, const int32_t* t_n, const int32_t* t_ld,
+                                const int64_t* t_bin_off, const int32_t* hmats, const int64_t* h_off,
+                                const int32_t* h_n, const int32_t* h_ld, const int64_t* h_bin_off, int32_t nchrom,
+                                const int32_t* h_sizes, const int64_t* h_hoff, const int32_t* h_hld,
+                                const int64_t* h_tbin, const int64_t* h_hbin, double* out, const int64_t* h_out_off,
+                                double* alpha, uint8_t* gapflag, int32_t* gapidx, int32_t* ngap, void* work,
+                                void* stream) {
+    HC_REQUIRE(nchrom > 0 && h_sizes && h_hoff && h_hld && h_tbin && h_hbin && h_out_off, "arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t t_nbins = h_tbin[nchrom], h_nbins = h_hbin[2 * nchrom];
+    int max_n = 0;
+    for (int c = 0; c < nchrom; ++c) max_n = h_sizes[c] > max_n ? h_sizes[c] : max_n;
+    if (t_nbins == 0) return HC_OK;
+    // scratch: row sums of T and H, nnz of H, alpha work, per-matrix two-step work
+    int64_t* rs_t = reinterpret_cast<int64_t*>(work);
+    int64_t* rs_h = rs_t + t_nbins;
+    double* awork = reinterpret_cast<double*>(rs_h + h_nbins);
+    int32_t* nz_h = reinterpret_cast<int32_t*>(awork + 2 * t_nbins);
+    void* mwork = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(nz_h + h_nbins) + 255) & ~(uintptr_t)255);
+
+    rowstats_batch_kernel<<<(unsigned)((t_nbins * 32 + 255) / 256), 256, 0, s>>>(tmats, t_off, t_n, t_ld, t_bin_off, nchrom, rs_t, nullptr);
+    HC_LAUNCH_CHECK();
+    rowstats_batch_kernel<<<(unsigned)((h_nbins * 32 + 255) / 256), 256, 0, s>>>(hmats, h_off, h_n, h_ld, h_bin_off, 2 * nchrom, rs_h, nz_h);
+    HC_LAUNCH_CHECK();
+    AlphaArgs a;
+    a.rs_t = rs_t; a.rs_m = rs_h; a.rs_p = rs_h; a.nnz_a = nz_h; a.nnz_b = nz_h; a.n = 0; a.ncols = 0;
+    a.gap_mode = HC_GAP_PERCENTILE; a.alpha = alpha; a.gf_a = gapflag; a.gf_b = gapflag; a.gi_a = gapidx; a.gi_b = gapidx;
+    a.ngap = ngap; a.work = awork; a.q25 = 25.0 / 100.0; a.q20 = 20.0 / 100.0;
+    a.t_bin_off = t_bin_off; a.h_bin_off = h_bin_off; a.nchrom = nchrom;
+    twostep_alpha_kernel<<<nchrom, 1024, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+
+    const size_t smem_tiles = (size_t)(T * T + T * LDB) * sizeof(int32_t);
+    const size_t smem_write = smem_tiles + (size_t)T * LDB * sizeof(double);
+    HC_CUDA(cudaFuncSetAttribute(sym_pass_kernel<PASS_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    for (int k = 0; k < 2 * nchrom; ++k) {
+        const int c = k % nchrom, hap = k / nchrom, n = h_sizes[c];
+        if (n == 0) continue;
+        const int nT = (n + T - 1) / T;
+        const int npairs = nT * (nT + 1) / 2;
+        TwoStepWork w = carve(mwork, n);
+        SymArgs g;
+        g.X = hmats + h_hoff[k]; g.ld = h_hld[k]; g.n = n; g.nT = nT;
+        g.alpha = alpha + h_tbin[c]; g.gapflag = gapflag + h_hbin[k]; g.has_gap = 0; g.ngap_dev = ngap + 2 * c + hap;
+        g.partial = w.partial; g.rs = w.rs; g.ra = w.ra; g.cta_partial = w.cta_partial; g.scalars = w.scalars;
+        g.out = out + h_out_off[k]; g.ld_out = n;
+        recip_alpha_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(g);
+        sym_pass_kernel<PASS_ROWSUM><<<npairs, TS_THREADS, smem_tiles, s>>>(g);
+        vc_scale_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(g);
+        sym_pass_kernel<PASS_TOTAL><<<npairs, TS_THREADS, smem_tiles, s>>>(g);
+        vc_rescale_factor_kernel<<<1, 1024, 0, s>>>(w.cta_partial, npairs, rs_h + h_hbin[k], n, w.scalars);
+        sym_pass_kernel<PASS_WRITE><<<npairs, TS_THREADS, smem_write, s>>>(g);
+        hc_count_launch(6);
+    }
+    HC_CUDA(cudaGetLastError());
     return HC_OK;
 }

@@ -425,3 +425,40 @@ def nccl_comm_init(uid: bytes, nranks: int, rank: int) -> int:
 
 def nccl_comm_destroy(comm: int):
     check(lib().hc_nccl_comm_destroy(C.c_void_p(comm)), "hc_nccl_comm_destroy")
+
+
+def twostep_batch(T: DenseBatch, H: DenseBatch):
+    """IntraChromMatrixCorrection (matrixBuilding.py:1026-1041) for all chromosomes in one library
+    call: ``T`` holds the nchrom traditional matrices, ``H`` the 2*nchrom haplotype matrices (all
+    maternal, then all paternal).  Returns (list of 2*nchrom (n, n) float64 device tensors in H's
+    order, list of 2*nchrom host gap-index arrays)."""
+    nchrom = len(T)
+    assert len(H) == 2 * nchrom and H.sizes[:nchrom] == T.sizes and H.sizes[nchrom:] == T.sizes
+    dev = T.device
+    sizes = T.sizes
+    out_off = np.concatenate([[0], np.cumsum([n * n for n in H.sizes])]).astype(np.int64)
+    out = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
+    alpha = torch.empty(max(T.nbins, 1), dtype=torch.float64, device=dev)
+    gapflag = torch.empty(max(H.nbins, 1), dtype=torch.uint8, device=dev)
+    gapidx = torch.empty(max(H.nbins, 1), dtype=torch.int32, device=dev)
+    ngap = torch.zeros(2 * nchrom, dtype=torch.int32, device=dev)
+    work = torch.empty(int(lib().hc_twostep_batch_work_bytes(T.nbins, H.nbins, max(sizes) if sizes else 0)),
+                       dtype=torch.uint8, device=dev)
+    i32 = lambda xs: (C.c_int32 * len(xs))(*[int(x) for x in xs])
+    i64 = lambda xs: (C.c_int64 * len(xs))(*[int(x) for x in xs])
+    check(lib().hc_twostep_batch(ptr(T.buf), ptr(T.mat_off), ptr(T.mat_n), ptr(T.mat_ld), ptr(T.bin_off),
+                                 ptr(H.buf), ptr(H.mat_off), ptr(H.mat_n), ptr(H.mat_ld), ptr(H.bin_off), nchrom,
+                                 i32(sizes), i64(H.offsets), i32(H.lds), i64(T.h_bin_off), i64(H.h_bin_off), ptr(out),
+                                 i64(out_off), ptr(alpha), ptr(gapflag), ptr(gapidx), ptr(ngap), ptr(work), stream_ptr()),
+          "hc_twostep_batch")
+    ng = ngap.cpu().numpy()                       # the only host round trip of the whole batch
+    gi = gapidx.cpu().numpy()
+    mats, gaps = [], []
+    for k in range(2 * nchrom):
+        n = H.sizes[k]
+        mats.append(out[int(out_off[k]):int(out_off[k + 1])].view(n, n))
+        c, hap = k % nchrom, k // nchrom
+        cnt = int(ng[2 * c + hap])
+        lo = int(H.h_bin_off[k])
+        gaps.append(gi[lo:lo + cnt].astype(np.int64) if cnt else np.array([]))
+    return mats, gaps

@@ -236,12 +236,17 @@ def TwoStepCorrection(TM, MM, PM):
 
 
 def IntraChromMatrixCorrection(Tra_Lib, Hap_Lib):
-    """matrixBuilding.py:1026-1041 -> (Nor_Lib, Gap_Lib) keyed 'M'+chrom / 'P'+chrom."""
+    """matrixBuilding.py:1026-1041 -> (Nor_Lib, Gap_Lib) keyed 'M'+chrom / 'P'+chrom.  All
+    chromosomes are corrected by one batched library call (``kernels.twostep_batch``)."""
+    chros = list(Tra_Lib.keys())
+    T = DenseBatch.from_numpy([np.asarray(Tra_Lib[c]) for c in chros])
+    H = DenseBatch.from_numpy([np.asarray(Hap_Lib["M" + c]) for c in chros] +
+                              [np.asarray(Hap_Lib["P" + c]) for c in chros])
+    mats, gaps = kernels.twostep_batch(T, H)
     Nor_Lib, Gap_Lib = {}, {}
-    for chro in Tra_Lib.keys():
-        a, b, ga, gb = TwoStepCorrection(Tra_Lib[chro], Hap_Lib["M" + chro], Hap_Lib["P" + chro])
-        Nor_Lib["M" + chro], Nor_Lib["P" + chro] = a, b
-        Gap_Lib["M" + chro], Gap_Lib["P" + chro] = ga, gb
+    for i, c in enumerate(chros):
+        Nor_Lib["M" + c], Nor_Lib["P" + c] = mats[i].cpu().numpy(), mats[len(chros) + i].cpu().numpy()
+        Gap_Lib["M" + c], Gap_Lib["P" + c] = gaps[i], gaps[len(chros) + i]
     return Nor_Lib, Gap_Lib
 
 

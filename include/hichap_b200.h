@@ -281,6 +281,20 @@ int hc_twostep_correct(const int32_t* X, int64_t ld, int32_t n, const double* al
                        const uint8_t* gapflag, int32_t has_gap, const int64_t* rowsum_x,
                        double* out, int64_t ld_out, void* work, void* stream);
 
+/* IntraChromMatrixCorrection (matrixBuilding.py:1026-1041) for a whole batch in one call, no host
+ * round trip: T = nchrom traditional matrices, H = 2*nchrom haplotype matrices (all maternal, then all
+ * paternal) of the same sides, both as dense batches (device tables + host copies h_*).  Outputs:
+ * out (fp64; matrix k of H at h_out_off[k], row-major n x n), alpha (per T bin), gapflag and gapidx (per
+ * H bin; ascending gap rows of matrix k at gapidx[h_hbin[k] ...]), ngap[2*nchrom] ordered (M_c, P_c).
+ * work: hc_twostep_batch_work_bytes(t_nbins, h_nbins, max_n). */
+int64_t hc_twostep_batch_work_bytes(int64_t t_nbins, int64_t h_nbins, int32_t max_n);
+int hc_twostep_batch(const int32_t* tmats, const int64_t* t_off, const int32_t* t_n, const int32_t* t_ld,
+                     const int64_t* t_bin_off, const int32_t* hmats, const int64_t* h_off, const int32_t* h_n,
+                     const int32_t* h_ld, const int64_t* h_bin_off, int32_t nchrom, const int32_t* h_sizes,
+                     const int64_t* h_hoff, const int32_t* h_hld, const int64_t* h_tbin, const int64_t* h_hbin,
+                     double* out, const int64_t* h_out_off, double* alpha, uint8_t* gapflag, int32_t* gapidx,
+                     int32_t* ngap, void* work, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Valid-pair text ingest (host, multithreaded): parses the 23-column
  * *_Valid.bed (layout 0: chromosomes in columns 1 and 8, fragment mid-points in columns 6 and 13;
