@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
             const int c = tx + 32 * b, gj = c0 + c;
             const bool vj = gj < a.n;
             const double ra_j = a.ra[gj];
-            const double sij = (double)sA[r * T + c] * ra_i;
-            const double sji = (double)tB[c * ldb + r] * ra_j;
+            const double sij = i32_to_f64(sA[r * T + c]) * ra_i;
+            const double sji = i32_to_f64(tB[c * ldb + r]) * ra_j;
             double sym;
             if (gi == gj) sym = sij;
             else if (!a.has_gap) sym = sij + sji;
