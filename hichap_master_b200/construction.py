@@ -28,9 +28,9 @@ import torch
 
 from . import _abi, kernels
 from .device import DenseBatch, PairColumns, require_cuda
-from .matrixBuilding import (GenomeWideMatrixCorrection, Get_Chro_Bins_Haplotypes, IntraMatrixToSparseDict,
-                             Load_Genome, Sort_Chromosomes, WholeMatrixToSparseDict, _bins_from_genome,
-                             _start_table, bin_traditional, chrom_offsets_from_bins, two_step_device)
+from .matrixBuilding import (GenomeWideMatrixCorrection, IntraMatrixToSparseDict, Load_Genome, Sort_Chromosomes,
+                             WholeMatrixToSparseDict, _bins_from_genome, _start_table, bin_traditional,
+                             chrom_offsets_from_bins)
 from .pairs import read_pair_files
 
 log = logging.getLogger(__name__)

@@ -98,10 +98,6 @@ __device__ __forceinline__ void red_add_s32_hint(int32_t* p, int v, uint64_t pol
     asm volatile("red.global.add.L2::cache_hint.s32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(policy) : "memory");
 }
 
-__device__ __forceinline__ void st_stream_v2f64(double* p, double a, double b) {
-    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

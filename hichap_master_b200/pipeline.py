@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _abi, kernels
+from . import kernels
 from ._abi import check, lib
 from .device import DenseBatch, PairColumns, ptr, require_cuda, stream_ptr
 

@@ -8,7 +8,7 @@ import io
 import numpy as np
 import pytest
 
-from conftest import CHROMS, SMALL_GENOME, SORTED_SMALL, load_golden, unflatten
+from conftest import CHROMS, SMALL_GENOME, load_golden, unflatten
 from hichap_master_b200 import synth
 from oracle import cooler_ice
 from oracle import hichap_oracle as ho

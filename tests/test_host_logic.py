@@ -5,7 +5,7 @@ import io
 import numpy as np
 import pytest
 
-from conftest import CHROMS, SMALL_GENOME, load_golden
+from conftest import CHROMS, SMALL_GENOME
 from hichap_master_b200 import pairs, synth
 from oracle import hichap_oracle as ho
 

@@ -3,9 +3,8 @@ the committed golden vectors that were produced by the UNMODIFIED reference run 
 oracle/ref_shim.py (oracle/make_golden.py).  Integer work is compared bit-exactly; floating
 point at 1e-12 (the reference's own NumPy arithmetic re-expressed, only summation order differs)."""
 import numpy as np
-import pytest
 
-from conftest import CHROMS, SMALL_GENOME, SORTED_SMALL, load_golden, unflatten
+from conftest import CHROMS, SORTED_SMALL, load_golden, unflatten
 from hichap_master_b200 import synth
 from oracle import cooler_ice
 from oracle import hichap_oracle as ho

@@ -5,7 +5,7 @@ import io
 import numpy as np
 import pytest
 
-from conftest import CHROMS, SMALL_GENOME
+from conftest import SMALL_GENOME
 from hichap_master_b200 import synth
 from oracle import hichap_oracle as ho
 from oracle import ref_shim
