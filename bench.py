@@ -185,7 +185,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     host = HostPairs(c1.cpu(), p1.cpu(), c1.cpu(), p2.cpu())
-    e2e_step = lambda: stage.run(stage.upload(host), RES, records=True, weights_to_host=True)
+    if os.environ.get("HC_E2E_CHUNKED", "1") == "1":     # chunked H2D overlapped with binning (default)
+        e2e_step = lambda: stage.run_from_host(host, RES, records=True, weights_to_host=True)
+    else:                                                   # A/B: whole-column upload, then the step
+        e2e_step = lambda: stage.run(stage.upload(host), RES, records=True, weights_to_host=True)
     for _ in range(max(1, min(args.warmup, 2))):
         o2 = e2e_step()
     e2e_steps = max(1, min(args.steps, 3))

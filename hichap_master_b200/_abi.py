@@ -48,6 +48,9 @@ SIGNATURES = {
     "hc_bin_band_work_bytes": (C.c_int64, [_I64, _I32]),
     "hc_bin_pairs_local_banded": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _I32,
                                             C.POINTER(_I32), _I32, _P, _P, _P]),
+    "hc_bin_band_begin": (C.c_int, [_P, _I64, _I32, _P]),
+    "hc_bin_band_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
+    "hc_bin_band_finish": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.POINTER(_I32), _I32, _P, _P]),
     "hc_widen_u8_i32": (C.c_int, [_P, _P, _I64, _P]),
     "hc_add_i32": (C.c_int, [_P, _P, _I64, _P]),
     "hc_bin_pairs_whole": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _I64, _P, _P]),

@@ -1,5 +1,6 @@
 // ABI glue: version, thread-local last-error string, launch counter.
 #include <stdarg.h>
+#include <string.h>
 #include <atomic>
 #include "hc_common.cuh"
 
@@ -30,6 +31,41 @@ extern "C" int hc_init(void) {
     unsigned long long thr = ~0ull;
     HC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     return HC_OK;
+}
+
+// Small device -> host reads (a convergence counter, a few offsets) that must not queue behind a
+// large cudaMemcpy on the device-to-host copy engine -- the upper-triangular records (1.4 GB for
+// C2) are copied out while the ICE loop runs, and a 4-byte cudaMemcpyAsync poll issued meanwhile
+// waited ~25 ms for that copy (tools/e2e_timeline.py).  A one-CTA kernel stores the words into a
+// pinned, mapped host mailbox straight over PCIe; the host waits for the stream and reads it.
+__global__ void mailbox_store_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+}
+
+namespace {
+struct Mailbox { uint32_t* host = nullptr; uint32_t* dev = nullptr; };
+constexpr size_t kMailboxBytes = 64 << 10;
+thread_local Mailbox g_mailbox;
+}  // namespace
+
+cudaError_t hc_read_small(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return cudaStreamSynchronize(s);
+    if (bytes > kMailboxBytes || (bytes & 3u) || (reinterpret_cast<uintptr_t>(src) & 3u)) {   // not mailbox-shaped
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+        return e == cudaSuccess ? cudaStreamSynchronize(s) : e;
+    }
+    Mailbox& m = g_mailbox;
+    if (!m.host) {
+        cudaError_t e = cudaHostAlloc((void**)&m.host, kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&m.dev, m.host, 0);
+        if (e != cudaSuccess) { m.host = nullptr; return e; }
+    }
+    mailbox_store_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(src), m.dev, (int)(bytes >> 2));
+    hc_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) memcpy(dst, m.host, bytes);
+    return e;
 }
 
 // dst += src (replicate merge of dense tiles, matrixBuilding.py:1700-1719)

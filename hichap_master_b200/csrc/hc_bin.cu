@@ -191,14 +191,27 @@ __device__ __forceinline__ void band_apply(const BandArgs& a, int c1, int p1, in
     else atomicAdd(a.mats + a.mat_off[c1] + (int64_t)lo * a.mat_ld[c1] + (lo + d), 1);
 }
 
+// U8: the chromosome columns are the uint8 columns a host parser ships over PCIe (255 = filtered,
+// rejected by the c1 >= nchrom test), read 4 at a time as one word
+template <bool U8>
 __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_band_kernel(BandArgs a) {
     const int64_t nvec = a.npairs / PAIRS_PER_THREAD;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long my_oob = 0;
     const uint64_t once = l2_policy_evict_first(), keep = l2_policy_evict_last();   // pairs stream through; the band stays
+    const uint8_t* c1b = reinterpret_cast<const uint8_t*>(a.in.c1);
+    const uint8_t* c2b = reinterpret_cast<const uint8_t*>(a.in.c2);
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const int4 c1 = ld_stream_v4_hint(a.in.c1 + 4 * v, once), p1 = ld_stream_v4_hint(a.in.p1 + 4 * v, once);
-        const int4 c2 = ld_stream_v4_hint(a.in.c2 + 4 * v, once), p2 = ld_stream_v4_hint(a.in.p2 + 4 * v, once);
+        int4 c1, c2;
+        if (U8) {
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(c1b + 4 * v), w2 = *reinterpret_cast<const uint32_t*>(c2b + 4 * v);
+            c1 = make_int4(w1 & 255, (w1 >> 8) & 255, (w1 >> 16) & 255, w1 >> 24);
+            c2 = make_int4(w2 & 255, (w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+        } else {
+            c1 = ld_stream_v4_hint(a.in.c1 + 4 * v, once);
+            c2 = ld_stream_v4_hint(a.in.c2 + 4 * v, once);
+        }
+        const int4 p1 = ld_stream_v4_hint(a.in.p1 + 4 * v, once), p2 = ld_stream_v4_hint(a.in.p2 + 4 * v, once);
         uint32_t mk = 0;
         if (a.in.mark) mk = *reinterpret_cast<const uint32_t*>(a.in.mark + 4 * v);
         band_apply(a, c1.x, p1.x, c2.x, p2.x, mk & 255, my_oob, keep);
@@ -208,7 +221,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_band_kernel(BandArgs a)
     }
     if (blockIdx.x == 0 && threadIdx.x < (int)(a.npairs - nvec * PAIRS_PER_THREAD)) {
         const int64_t i = nvec * PAIRS_PER_THREAD + threadIdx.x;
-        band_apply(a, a.in.c1[i], a.in.p1[i], a.in.c2[i], a.in.p2[i], a.in.mark ? a.in.mark[i] : 0, my_oob, keep);
+        const int x = U8 ? (int)c1b[i] : a.in.c1[i], y = U8 ? (int)c2b[i] : a.in.c2[i];
+        band_apply(a, x, a.in.p1[i], y, a.in.p2[i], a.in.mark ? a.in.mark[i] : 0, my_oob, keep);
     }
     if (a.oob) {
         my_oob = (unsigned long long)warp_sum_ll((long long)my_oob);
@@ -366,17 +380,55 @@ extern "C" int64_t hc_bin_band_work_bytes(int64_t nbins, int32_t band_width) {
     return (int64_t)sizeof(int32_t) * (nbins > 0 ? nbins : 1) * band_width;
 }
 
-extern "C" int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
-                                         const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
-                                         int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
-                                         const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
-                                         const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
-                                         void* work, void* stream) {
+namespace {
+int band_shift(int band_width) { int sh = 0; while ((1 << sh) < band_width) ++sh; return sh; }
+bool band_width_ok(int bw) { return bw >= 32 && bw <= 1024 && (bw & (bw - 1)) == 0; }
+}  // namespace
+
+// The three phases of banded binning, separately callable so that pairs can be accumulated chunk by
+// chunk while later chunks are still crossing PCIe: begin (zero the band) -> accumulate xN -> finish
+// (merge the band into the tiles, mirror upper -> lower).
+extern "C" int hc_bin_band_begin(void* work, int64_t nbins, int32_t band_width, void* stream) {
+    HC_REQUIRE(nbins >= 0 && band_width_ok(band_width), "band_width: power of two in [32,1024]");
+    if (nbins == 0) return HC_OK;
+    HC_REQUIRE(work != nullptr, "work");
+    HC_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t) * (size_t)nbins * band_width, (cudaStream_t)stream));
+    return HC_OK;
+}
+
+extern "C" int hc_bin_band_accumulate(const void* c1, const int32_t* p1, const void* c2, const int32_t* p2,
+                                      const uint8_t* mark, int64_t npairs, int32_t chrom_is_u8, int32_t res, int32_t mode,
+                                      int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                      const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
+                                      int32_t band_width, unsigned long long* oob, void* work, void* stream) {
     HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0, "npairs>=0, res>0, nchrom>0");
     HC_REQUIRE(mode == HC_BIN_SYM_ALL || mode == HC_BIN_SYM_BOTH, "banded binning is for the symmetric modes");
     HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
-    HC_REQUIRE(nchrom <= PART_MAX_BUCKETS && h_mat_n != nullptr, "at most 256 chromosomes; h_mat_n");
-    HC_REQUIRE(band_width >= 32 && band_width <= 1024 && (band_width & (band_width - 1)) == 0, "band_width: power of two in [32,1024]");
+    HC_REQUIRE(band_width_ok(band_width), "band_width: power of two in [32,1024]");
+    HC_REQUIRE(!chrom_is_u8 || nchrom <= 255, "uint8 chromosome columns hold at most 255 chromosomes");
+    if (npairs == 0) return HC_OK;
+    HC_REQUIRE(aligned16(p1) && aligned16(p2), "position columns must be 16-byte aligned");
+    if (chrom_is_u8) HC_REQUIRE(((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 3u) == 0, "uint8 chromosome columns must be 4-byte aligned");
+    else HC_REQUIRE(aligned16(c1) && aligned16(c2), "pair columns must be 16-byte aligned");
+    HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    BandArgs a;
+    a.in = PairCols{reinterpret_cast<const int32_t*>(c1), p1, reinterpret_cast<const int32_t*>(c2), p2, mark};
+    a.npairs = npairs; a.res = make_fast_div((uint32_t)res); a.mode = mode;
+    a.nchrom = nchrom; a.mats = mats; a.mat_off = mat_off; a.mat_n = mat_n; a.mat_ld = mat_ld; a.bin_off = bin_off;
+    a.band = reinterpret_cast<int32_t*>(work); a.oob = oob;
+    a.bw_shift = band_shift(band_width);
+    if (chrom_is_u8) bin_pairs_band_kernel<true><<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
+    else bin_pairs_band_kernel<false><<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int hc_bin_band_finish(int32_t* mats, const int64_t* mat_off, const int32_t* mat_n, const int32_t* mat_ld,
+                                  const int64_t* bin_off, int32_t nchrom, const int32_t* h_mat_n, int32_t band_width,
+                                  void* work, void* stream) {
+    HC_REQUIRE(nchrom > 0 && nchrom <= PART_MAX_BUCKETS && h_mat_n != nullptr, "at most 256 chromosomes; h_mat_n");
+    HC_REQUIRE(band_width_ok(band_width), "band_width: power of two in [32,1024]");
     MirrorTab mtab;
     mtab.nprob = nchrom;
     mtab.start[0] = 0;
@@ -389,19 +441,12 @@ extern "C" int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, c
         HC_REQUIRE(nxt < (1ll << 31), "too many tiles");
         mtab.start[p + 1] = (int)nxt;
     }
-    if (npairs == 0 || nbins == 0) return HC_OK;
-    HC_REQUIRE(aligned16(c1) && aligned16(p1) && aligned16(c2) && aligned16(p2), "pair columns must be 16-byte aligned");
-    HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
+    if (nbins == 0) return HC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    BandArgs a;
-    a.in = PairCols{c1, p1, c2, p2, mark}; a.npairs = npairs; a.res = make_fast_div((uint32_t)res); a.mode = mode;
+    BandArgs a{};
     a.nchrom = nchrom; a.mats = mats; a.mat_off = mat_off; a.mat_n = mat_n; a.mat_ld = mat_ld; a.bin_off = bin_off;
-    a.band = reinterpret_cast<int32_t*>(work); a.oob = oob;
-    a.bw_shift = 0;
-    while ((1 << a.bw_shift) < band_width) ++a.bw_shift;
-    HC_CUDA(cudaMemsetAsync(a.band, 0, sizeof(int32_t) * (size_t)nbins * band_width, s));
-    bin_pairs_band_kernel<<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
-    HC_LAUNCH_CHECK();
+    a.band = reinterpret_cast<int32_t*>(work);
+    a.bw_shift = band_shift(band_width);
     band_merge_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, s>>>(a, nbins);
     HC_LAUNCH_CHECK();
     if (mtab.start[nchrom] > 0) {
@@ -409,6 +454,23 @@ extern "C" int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, c
         HC_LAUNCH_CHECK();
     }
     return HC_OK;
+}
+
+extern "C" int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                                         const uint8_t* mark, int64_t npairs, int32_t res, int32_t mode,
+                                         int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                                         const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
+                                         const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
+                                         void* work, void* stream) {
+    HC_REQUIRE(nchrom > 0 && nchrom <= PART_MAX_BUCKETS && h_mat_n != nullptr, "at most 256 chromosomes; h_mat_n");
+    int64_t nbins = 0;
+    for (int p = 0; p < nchrom; ++p) nbins += h_mat_n[p] > 0 ? h_mat_n[p] : 0;
+    if (npairs == 0 || nbins == 0) return HC_OK;
+    int rc = hc_bin_band_begin(work, nbins, band_width, stream);
+    if (rc == HC_OK) rc = hc_bin_band_accumulate(c1, p1, c2, p2, mark, npairs, 0, res, mode, mats, mat_off, mat_n, mat_ld,
+                                                 bin_off, nchrom, band_width, oob, work, stream);
+    if (rc == HC_OK) rc = hc_bin_band_finish(mats, mat_off, mat_n, mat_ld, bin_off, nchrom, h_mat_n, band_width, work, stream);
+    return rc;
 }
 
 extern "C" int hc_bin_pairs_whole(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,

@@ -7,6 +7,8 @@
 
 void hc_set_error(const char* fmt, ...);
 void hc_count_launch(int n = 1);
+// synchronous small device->host read through a pinned mailbox (no copy engine; see hc_abi.cu)
+cudaError_t hc_read_small(void* dst, const void* src, size_t bytes, cudaStream_t s);
 
 #define HC_CUDA(call)                                                                       \
     do {                                                                                    \

@@ -323,8 +323,7 @@ extern "C" int hc_ice_dense_marginals(const int32_t* mats, const int64_t* mat_of
                                       int32_t ignore_diags, double* nnz_marg, double* marg, void* stream) {
     HC_REQUIRE(nprob > 0 && ignore_diags >= 0, "nprob>0, ignore_diags>=0");
     int64_t total = 0;
-    HC_CUDA(cudaMemcpyAsync(&total, bin_off + nprob, sizeof(int64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    HC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    HC_CUDA(hc_read_small(&total, bin_off + nprob, sizeof(int64_t), (cudaStream_t)stream));
     if (total == 0) return HC_OK;
     const int64_t blocks = (total * 32 + 255) / 256;
     ice_dense_marginals_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -397,8 +396,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     // kernel can read the bias of any 4-column group with two aligned 16-byte loads and never
     // needs a column bound check (matrix padding columns are zero, padded bias entries are zero)
     std::vector<int32_t> h_ld(nprob);
-    HC_CUDA(cudaMemcpyAsync(h_ld.data(), mat_ld, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
+    HC_CUDA(hc_read_small(h_ld.data(), mat_ld, sizeof(int32_t) * nprob, s));
     std::vector<int64_t> h_pad(nprob + 1, 0);
     for (int p = 0; p < nprob; ++p) {
         if (h_ld[p] < h_mat_n[p] || (h_ld[p] & 127) != 0) {
@@ -514,14 +512,12 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         }
         hc_count_launch(2 * poll);
         launches += 2 * poll;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_ndone, A.n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = hc_read_small(&h_ndone, A.n_done, sizeof(int32_t), s);   // not a memcpy: see hc_read_small
         if (e == cudaSuccess && h_ndone >= nonempty) break;
         if (e == cudaSuccess && h_ndone != seen_done) {
             // drop the converged chromosomes from the work list (their items would only be skipped)
             seen_done = h_ndone;
-            e = cudaMemcpyAsync(h_done.data(), A.done, sizeof(int32_t) * nprob, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            e = hc_read_small(h_done.data(), A.done, sizeof(int32_t) * nprob, s);
             if (e == cudaSuccess) { build_items(); e = upload_items(); }
         }
         if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }

@@ -426,8 +426,7 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
         ice_stat_update_kernel<<<sgrid, STAT_THREADS, 0, s>>>(st);
         hc_count_launch(3); launches += 3;
         if (k % poll == 0 || k == P->max_iters) {
-            cudaError_t e = cudaMemcpyAsync(&h_done, n_done, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            cudaError_t e = hc_read_small(&h_done, n_done, sizeof(int32_t), s);
             if (e != cudaSuccess) { hc_set_error("hc_ice_csr_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
             if (h_done >= nonempty) break;
         }

@@ -70,6 +70,40 @@ def bin_pairs_local_banded(pairs: PairColumns, res: int, batch: DenseBatch, mode
     return work
 
 
+class BandedBinning:
+    """begin -> accumulate(chunk) x N -> finish: banded binning fed chunk by chunk (e.g. while later
+    chunks are still in flight over PCIe).  Chromosome columns may be int32 or uint8 (255 = filtered)."""
+
+    def __init__(self, batch: DenseBatch, res: int, mode=_abi.HC_BIN_SYM_ALL, work=None, band_width=None):
+        if len(batch) > 256 or mode == _abi.HC_BIN_ONESIDED:
+            raise ValueError("banded binning: symmetric modes, at most 256 matrices")
+        self.batch, self.res, self.mode = batch, int(res), int(mode)
+        self.bw = int(os.environ.get("HC_BIN_BAND", "128")) if band_width is None else int(band_width)
+        self.oob = _oob_counter(batch.device)
+        nbytes = int(lib().hc_bin_band_work_bytes(batch.nbins, self.bw))
+        if work is None or work.numel() < nbytes:
+            work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=batch.device)
+        self.work = work
+        check(lib().hc_bin_band_begin(ptr(work), batch.nbins, self.bw, stream_ptr()), "hc_bin_band_begin")
+
+    def accumulate(self, c1, p1, c2, p2, mark=None):
+        b = self.batch
+        u8 = c1.dtype == torch.uint8
+        assert c2.dtype == c1.dtype and p1.dtype == torch.int32 and p2.dtype == torch.int32
+        check(lib().hc_bin_band_accumulate(ptr(c1), ptr(p1), ptr(c2), ptr(p2), ptr(mark), int(p1.numel()), int(u8),
+                                           self.res, self.mode, ptr(b.buf), ptr(b.mat_off), ptr(b.mat_n), ptr(b.mat_ld),
+                                           ptr(b.bin_off), len(b), self.bw, ptr(self.oob), ptr(self.work), stream_ptr()),
+              "hc_bin_band_accumulate")
+
+    def finish(self, check_bounds=True):
+        b = self.batch
+        check(lib().hc_bin_band_finish(ptr(b.buf), ptr(b.mat_off), ptr(b.mat_n), ptr(b.mat_ld), ptr(b.bin_off), len(b),
+                                       b.h_mat_n, self.bw, ptr(self.work), stream_ptr()), "hc_bin_band_finish")
+        if check_bounds:
+            _raise_oob(self.oob, "intra-chromosomal")
+        return self.work
+
+
 def bin_pairs_whole(pairs: PairColumns, res: int, start1, start2, whole: DenseBatch,
                     mode=_abi.HC_BIN_SYM_ALL, check_bounds=True):
     """Accumulate pairs into the single genome-wide matrix ``whole`` (a 1-matrix batch) with

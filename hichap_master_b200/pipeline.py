@@ -50,6 +50,7 @@ class LocalStage:
         self.banded = True      # banded binning (hc_bin_pairs_local_banded)
         self.bin_work = None
         self.side = torch.cuda.Stream(device=self.dev)
+        self.copy = torch.cuda.Stream(device=self.dev)
 
     def upload(self, hp: HostPairs) -> PairColumns:
         assert hp.n <= self.max_pairs
@@ -70,6 +71,38 @@ class LocalStage:
             self.bin_work = kernels.bin_pairs_local_banded(pairs, res, b, check_bounds=False, work=self.bin_work)
         else:
             kernels.bin_pairs_local(pairs, res, b, check_bounds=False)
+        return self._after_binning(records, weights_to_host, **ice_kw)
+
+    def run_from_host(self, hp: HostPairs, res: int, records=False, weights_to_host=True, chunk_pairs=1 << 24,
+                      **ice_kw):
+        """``run`` fed straight from pinned host columns: the pairs cross PCIe in chunks on a copy
+        stream and every chunk is binned (uint8 chromosome columns read as they are) while the next
+        ones are in flight, so that only the last chunk's binning is exposed after the transfer."""
+        assert hp.n <= self.max_pairs
+        b, n = self.batch, hp.n
+        main = torch.cuda.current_stream()
+        b.buf.zero_()
+        bb = kernels.BandedBinning(b, res, work=self.bin_work)
+        ready = torch.cuda.Event()
+        ready.record(main)                 # the device columns may still be read by work queued earlier on `main`
+        self.copy.wait_event(ready)
+        chunk = max(16, int(chunk_pairs) // 16 * 16)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            with torch.cuda.stream(self.copy):
+                self.chrom8[0][lo:hi].copy_(hp.c1[lo:hi], non_blocking=True)
+                self.cols[1][lo:hi].copy_(hp.p1[lo:hi], non_blocking=True)
+                self.chrom8[1][lo:hi].copy_(hp.c2[lo:hi], non_blocking=True)
+                self.cols[3][lo:hi].copy_(hp.p2[lo:hi], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self.copy)
+            main.wait_event(landed)
+            bb.accumulate(self.chrom8[0][lo:hi], self.cols[1][lo:hi], self.chrom8[1][lo:hi], self.cols[3][lo:hi])
+        self.bin_work = bb.finish(check_bounds=False)
+        return self._after_binning(records, weights_to_host, **ice_kw)
+
+    def _after_binning(self, records, weights_to_host, **ice_kw):
+        b = self.batch
         recs, d2h = None, 0
         main = torch.cuda.current_stream()
         if records:

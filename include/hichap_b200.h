@@ -77,6 +77,21 @@ int hc_bin_pairs_local_banded(const int32_t* c1, const int32_t* p1, const int32_
                               const int32_t* h_mat_n, int32_t band_width, unsigned long long* oob,
                               void* work, void* stream);
 
+/* The same three phases, separately callable, so that a caller can accumulate pairs chunk by chunk
+ * while later chunks are still crossing PCIe (the reference reads the whole bed stream before it has
+ * a matrix, matrixBuilding.py:573-592): begin zeroes the band; accumulate may be called any number of
+ * times (chrom_is_u8 != 0: c1/c2 are uint8 columns, 255 = filtered, 4-byte aligned; else int32 columns);
+ * finish merges the band into the tiles and mirrors the upper triangle. */
+int hc_bin_band_begin(void* work, int64_t nbins, int32_t band_width, void* stream);
+int hc_bin_band_accumulate(const void* c1, const int32_t* p1, const void* c2, const int32_t* p2,
+                           const uint8_t* mark, int64_t npairs, int32_t chrom_is_u8, int32_t res, int32_t mode,
+                           int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
+                           const int32_t* mat_ld, const int64_t* bin_off, int32_t nchrom,
+                           int32_t band_width, unsigned long long* oob, void* work, void* stream);
+int hc_bin_band_finish(int32_t* mats, const int64_t* mat_off, const int32_t* mat_n, const int32_t* mat_ld,
+                       const int64_t* bin_off, int32_t nchrom, const int32_t* h_mat_n, int32_t band_width,
+                       void* work, void* stream);
+
 /* Chromosome-id columns may cross PCIe as uint8 (255 = filtered chromosome): widen to the int32
  * columns the binning entry points take (255 -> -1). */
 int hc_widen_u8_i32(const uint8_t* src, int32_t* dst, int64_t n, void* stream);

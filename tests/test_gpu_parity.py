@@ -366,3 +366,31 @@ def test_banded_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
                       np.array([5], np.int32))
     with pytest.raises(IndexError):
         kernels.bin_pairs_local_banded(bad, res, DenseBatch(sizes, cuda_device))
+
+
+@pytest.mark.parametrize("n,chunk", [(0, 64), (5, 16), (100_003, 4096), (100_003, 1 << 24)])
+def test_stage_from_host_chunks_equals_whole_upload(mb, cuda_device, n, chunk):
+    """`LocalStage.run_from_host` (chunked H2D on a copy stream, uint8 chromosome columns binned as
+    they land) gives the same tiles, records and weights as upload-then-run, and as the oracle."""
+    from hichap_master_b200.pipeline import HostPairs, LocalStage
+    genome = {c: l for c, l in SMALL_GENOME.items() if c != "M"}
+    order = list(genome)
+    res = 40000
+    c1, p1, c2, p2 = synth.genome_pairs(genome, order, max(n, 1), 77, trans_frac=0.1)
+    c1, p1, c2, p2 = c1[:n].copy(), p1[:n], c2[:n].copy(), p2[:n]
+    if n > 10:
+        c1[::13] = -1
+    sizes = [genome[c] // res + 1 for c in order]
+    host = HostPairs(c1, p1, c2, p2)
+    st = LocalStage(sizes, max(n, 16), cuda_device)
+    o1 = st.run(st.upload(host), res, records=True)
+    tiles1 = [st.batch.to_numpy(i).copy() for i in range(len(sizes))]
+    w1 = o1["bias"].cpu().numpy().copy()
+    rec1 = [r.copy() for r in o1["records"]]
+    o2 = st.run_from_host(host, res, records=True, chunk_pairs=chunk)
+    keep = (c1 >= 0) & (c2 >= 0)
+    exp = ho.bin_local_dense(c1[keep], p1[keep], c2[keep], p2[keep], sizes, res)
+    for i in range(len(sizes)):
+        assert np.array_equal(st.batch.to_numpy(i), tiles1[i]) and np.array_equal(tiles1[i], exp[i])
+        assert np.array_equal(o2["records"][i], rec1[i])
+    assert np.array_equal(o2["bias"].cpu().numpy(), w1, equal_nan=True)
