@@ -51,6 +51,8 @@ SIGNATURES = {
     "hc_bin_band_begin": (C.c_int, [_P, _I64, _I32, _P]),
     "hc_bin_band_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "hc_bin_band_finish": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.POINTER(_I32), _I32, _P, _P]),
+    "hc_impute_inter": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _I32, _I64, _I32, _P, _P, _I32,
+                                  _I64, C.c_double, _I32, _I64, _P, _P, _P]),
     "hc_widen_u8_i32": (C.c_int, [_P, _P, _I64, _P]),
     "hc_add_i32": (C.c_int, [_P, _P, _I64, _P]),
     "hc_bin_pairs_whole": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _I64, _P, _P]),

@@ -14,8 +14,8 @@ them, plus the ``weight`` vector and balancing stats that ``cooler balance`` wou
 (consumed at StructureFind.py:1988-1992).
 
 Deviations (documented in DESIGN.md): allelic mode accepts a single replicate (the reference
-raises TypeError there, matrixBuilding.py:1676-1683); inter-chromosomal imputation
-(:1302-1378, :1416-1492) is not performed.
+raises TypeError there, matrixBuilding.py:1676-1683).  Inter-chromosomal imputation
+(:1302-1378, :1416-1492) is performed bug for bug (``matrixBuilding.impute_inter_chromosomal``).
 """
 from __future__ import annotations
 
@@ -30,7 +30,7 @@ from . import _abi, kernels
 from .device import DenseBatch, PairColumns, require_cuda
 from .matrixBuilding import (GenomeWideMatrixCorrection, IntraMatrixToSparseDict, Load_Genome, Sort_Chromosomes,
                              WholeMatrixToSparseDict, _bins_from_genome, _start_table, bin_traditional,
-                             chrom_offsets_from_bins)
+                             chrom_offsets_from_bins, impute_inter_chromosomal)
 from .pairs import read_pair_files
 
 log = logging.getLogger(__name__)
@@ -184,7 +184,7 @@ class HaplotypeData:
         return out
 
 
-def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev):
+def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev, imputation=(10000000, 2, 0.9)):
     """Binning part of HaplotypeMatrixBuilding (matrixBuilding.py:1079-1500) for one replicate."""
     order = Sort_Chromosomes(genome)
     nchrom = len(order)
@@ -210,6 +210,7 @@ def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev):
             view = _sub_batch(imp, hap * nchrom, nchrom)
             kernels.bin_pairs_local(cols[tag], res, view, _abi.HC_BIN_ONESIDED)           # :1295-1301
         data.un_local[res], data.imp_local[res] = un, imp
+    starts, un_w, imp_w = {}, {}, {}
     for res in wholeRes:
         hb, htot = _bins_from_genome(genome, res, [("M" + c, c) for c in order] + [("P" + c, c) for c in order])
         sm = _start_table(hb, ["M" + c for c in order], dev)
@@ -225,6 +226,9 @@ def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev):
         kernels.bin_pairs_whole(cols["P_P"], res, sp, sp, imp, _abi.HC_BIN_ONESIDED)      # :1399-1407 (cis)
         data.un_whole[res], data.imp_whole[res] = (hb, un), (hb, imp)
         data.hap_bins[res] = hb
+        starts[res], un_w[res], imp_w[res] = (sm, sp), un, imp
+    # inter-chromosomal one-sided contacts: neighbourhood vote on the un-imputed matrix (:1302-1378, :1416-1492)
+    impute_inter_chromosomal(un_w, imp_w, cols["M_M"], cols["P_P"], starts, wholeRes, *imputation)
     return data
 
 
@@ -315,8 +319,8 @@ def WholeMatrixToSparseDict_float(Bins, Matrix):
 def HaplotypeMatrixBuilding(OutPath, BedPath, genomeSize, wholeRes, localRes, Imputation_region=10000000,
                             Imputation_min=2, Imputation_ratio=0.9, chroms=["#", "X"], _return_device=False):
     """matrixBuilding.py:1044-1638 for one replicate.  Returns (prefix, DataSets) like the
-    reference (NumPy matrices); the Imputation_* parameters are accepted for signature
-    compatibility -- inter-chromosomal imputation is not performed (see module docstring)."""
+    reference (NumPy matrices), inter-chromosomal imputation included (bug for bug, see
+    ``matrixBuilding.impute_inter_chromosomal``)."""
     dev = require_cuda()
     files = sorted(i for i in os.listdir(BedPath)
                    if any((t + ".bed") in i for t in ("Bi_Allelic", "M_M", "M_P", "P_P", "P_M")))
@@ -330,7 +334,8 @@ def HaplotypeMatrixBuilding(OutPath, BedPath, genomeSize, wholeRes, localRes, Im
             raise Exception("Missing file %s.bed in %s" % (tag, BedPath))            # :1075
     files = [os.path.join(BedPath, f) for f in files]
     genome = Load_Genome(genomeSize, chroms)
-    data = _haplotype_counts(files, genome, wholeRes, localRes, chroms, dev)
+    data = _haplotype_counts(files, genome, wholeRes, localRes, chroms, dev,
+                             (Imputation_region, Imputation_min, Imputation_ratio))
     _haplotype_outputs(OutPath, prefix, genome, data, wholeRes, localRes)
     if _return_device:
         return prefix, data

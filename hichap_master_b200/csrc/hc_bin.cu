@@ -363,8 +363,8 @@ extern "C" int hc_bin_pairs_local(const int32_t* c1, const int32_t* p1, const in
                                   int32_t nchrom, unsigned long long* oob, void* stream) {
     HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0, "npairs>=0, res>0, nchrom>0");
     HC_REQUIRE(mode >= HC_BIN_SYM_ALL && mode <= HC_BIN_ONESIDED, "mode");
-    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     if (npairs == 0) return HC_OK;
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     HC_REQUIRE(aligned16(c1) && aligned16(p1) && aligned16(c2) && aligned16(p2), "pair columns must be 16-byte aligned");
     HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
     PairCols in{c1, p1, c2, p2, mark};
@@ -403,10 +403,10 @@ extern "C" int hc_bin_band_accumulate(const void* c1, const int32_t* p1, const v
                                       int32_t band_width, unsigned long long* oob, void* work, void* stream) {
     HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0, "npairs>=0, res>0, nchrom>0");
     HC_REQUIRE(mode == HC_BIN_SYM_ALL || mode == HC_BIN_SYM_BOTH, "banded binning is for the symmetric modes");
-    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     HC_REQUIRE(band_width_ok(band_width), "band_width: power of two in [32,1024]");
     HC_REQUIRE(!chrom_is_u8 || nchrom <= 255, "uint8 chromosome columns hold at most 255 chromosomes");
     if (npairs == 0) return HC_OK;
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     HC_REQUIRE(aligned16(p1) && aligned16(p2), "position columns must be 16-byte aligned");
     if (chrom_is_u8) HC_REQUIRE(((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 3u) == 0, "uint8 chromosome columns must be 4-byte aligned");
     else HC_REQUIRE(aligned16(c1) && aligned16(c2), "pair columns must be 16-byte aligned");
@@ -479,8 +479,8 @@ extern "C" int hc_bin_pairs_whole(const int32_t* c1, const int32_t* p1, const in
                                   int32_t total, int64_t ld, unsigned long long* oob, void* stream) {
     HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0 && total > 0 && ld >= total, "sizes");
     HC_REQUIRE(mode >= HC_BIN_SYM_ALL && mode <= HC_BIN_ONESIDED, "mode");
-    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     if (npairs == 0) return HC_OK;
+    HC_REQUIRE(mode == HC_BIN_SYM_ALL || mark != nullptr, "mark column required for this mode");
     HC_REQUIRE(aligned16(c1) && aligned16(p1) && aligned16(c2) && aligned16(p2), "pair columns must be 16-byte aligned");
     HC_REQUIRE(mark == nullptr || (reinterpret_cast<uintptr_t>(mark) & 3u) == 0, "mark must be 4-byte aligned");
     PairCols in{c1, p1, c2, p2, mark};

@@ -104,6 +104,19 @@ class BandedBinning:
         return self.work
 
 
+def impute_inter(pairs: PairColumns, res: int, start_m, start_p, own_is_p: bool, un: DenseBatch, imp: DenseBatch,
+                 half_width: int, nb_i, nb_j, imin: int, ratio: float, stale_state=0, stale_sum=0,
+                 last_qualifying=None, stale_needed=None):
+    """Inter-chromosomal imputation of the one-sided lines of an M_M / P_P bed on the genome-wide
+    haplotype matrix (``hc_impute_inter``; matrixBuilding.py:1302-1378, :1416-1492)."""
+    assert len(un) == 1 and len(imp) == 1 and un.sizes[0] == imp.sizes[0] and un.lds[0] == imp.lds[0]
+    check(lib().hc_impute_inter(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2), ptr(pairs.mark), pairs.n,
+                                int(res), ptr(start_m), ptr(start_p), int(start_m.numel()), int(bool(own_is_p)),
+                                ptr(un.buf), ptr(imp.buf), un.sizes[0], un.lds[0], int(half_width), ptr(nb_i), ptr(nb_j),
+                                int(nb_i.numel()), int(imin), float(ratio), int(stale_state), int(stale_sum),
+                                ptr(last_qualifying), ptr(stale_needed), stream_ptr()), "hc_impute_inter")
+
+
 def bin_pairs_whole(pairs: PairColumns, res: int, start1, start2, whole: DenseBatch,
                     mode=_abi.HC_BIN_SYM_ALL, check_bounds=True):
     """Accumulate pairs into the single genome-wide matrix ``whole`` (a 1-matrix batch) with

@@ -203,6 +203,81 @@ def bin_haplotype_local(pairs: PairColumns, genome: dict, res: int, onesided: bo
     return L
 
 
+def GetNeighborhoodIndex(L):
+    """matrixBuilding.py:721-732: window indices (i, j) of a (2L+1)x(2L+1) window closer than
+    sqrt(L) to (L+1, L+1) -- the reference's centre, one off the window centre."""
+    i, j = np.mgrid[0:2 * L + 1, 0:2 * L + 1]
+    near = np.sqrt(((i - (L + 1)) ** 2 + (j - (L + 1)) ** 2).astype(np.float64)) < np.sqrt(np.float64(L))
+    return [int(x) for x in i[near]], [int(x) for x in j[near]]
+
+
+def impute_inter_chromosomal(un: dict, imp: dict, mm: PairColumns, pp: PairColumns, starts: dict, wholeRes,
+                             Imputation_region, Imputation_min, Imputation_ratio):
+    """Inter-chromosomal branches of the imputation loops (matrixBuilding.py:1302-1378 for the M_M
+    file, :1416-1492 for P_P) on the genome-wide haplotype matrices, bug for bug.
+
+    un / imp: {res: one-matrix DenseBatch} (un-imputed, read only / imputed, credited);
+    starts: {res: (start_M, start_P)} device int64 tables; mm / pp: the bed columns in FILE order.
+
+    The P_P R1 branch of the reference votes with the window object `M_M_sub` left behind by the M_M
+    loop (:1448).  That window belongs to the last M_M line -- and, within it, the last resolution
+    of `wholeRes` -- that reached the window cut; it is located on the device (atomic max of the line
+    index), fetched, and its disc sum per resolution handed to the P_P pass.  Where the reference
+    would raise (no such line: NameError; stale window of a coarser resolution too small for this
+    resolution's indices: IndexError) the same exception is raised here if a P_P R1 line gets that far.
+    """
+    dev = mm.device
+    wholeRes = list(wholeRes)
+    half = {res: int(Imputation_region) // res for res in wholeRes}
+    nb = {}
+    for res in wholeRes:
+        ii, jj = GetNeighborhoodIndex(half[res])
+        nb[res] = (torch.tensor(ii, dtype=torch.int32, device=dev), torch.tensor(jj, dtype=torch.int32, device=dev), ii, jj)
+    last = torch.full((len(wholeRes),), -1, dtype=torch.int64, device=dev)
+    for k, res in enumerate(wholeRes):
+        kernels.impute_inter(mm, res, starts[res][0], starts[res][1], False, un[res], imp[res], half[res], nb[res][0],
+                             nb[res][1], Imputation_min, Imputation_ratio, last_qualifying=last[k:k + 1])
+    if pp.n == 0:
+        return
+    # ---- the stale `M_M_sub` window -------------------------------------------------------------
+    h_last = last.cpu().numpy()
+    line = int(h_last.max()) if len(h_last) else -1
+    stale = None
+    if line >= 0:
+        k = max(i for i in range(len(wholeRes)) if h_last[i] == line)
+        res = wholeRes[k]
+        ca, pa, cb, pb, mk = (int(t[line].item()) for t in (mm.c1, mm.p1, mm.c2, mm.p2, mm.mark))
+        sm, sp = starts[res][0].cpu().numpy(), starts[res][1].cpu().numpy()
+        b1, b2, s = pa // res, pb // res, half[res]
+        if mk == 1:
+            r0, c0 = b1 + int(sm[ca]), b2 + int(sm[cb])          # Matrix[bin1 +- s, M_bin2 +- s]   (:1327)
+        else:
+            r0, c0 = b1 + int(sm[cb]), b2 + int(sm[ca])          # Matrix[M_bin1 +- s, bin2 +- s]   (:1363)
+        n, ld = un[res].sizes[0], un[res].lds[0]
+        U = un[res].buf[un[res].offsets[0]:un[res].offsets[0] + n * ld].view(n, ld)
+        stale = U[r0 - s:r0 + s + 1, c0 - s:c0 + s + 1].cpu().numpy().astype(np.int64)
+    needed = torch.zeros(len(wholeRes), dtype=torch.int32, device=dev)
+    states = []
+    for k, res in enumerate(wholeRes):
+        ii, jj = nb[res][2], nb[res][3]
+        if stale is None:
+            state, ksum = 1, 0
+        elif ii and (max(ii) >= stale.shape[0] or max(jj) >= stale.shape[1]):
+            state, ksum = 2, 0
+        else:
+            state, ksum = 0, int(stale[ii, jj].sum())
+        states.append(state)
+        kernels.impute_inter(pp, res, starts[res][0], starts[res][1], True, un[res], imp[res], half[res], nb[res][0],
+                             nb[res][1], Imputation_min, Imputation_ratio, stale_state=state, stale_sum=ksum,
+                             stale_needed=needed[k:k + 1])
+    h_needed = needed.cpu().numpy()
+    for k, res in enumerate(wholeRes):
+        if h_needed[k] and states[k] == 1:
+            raise NameError("name 'M_M_sub' is not defined")          # what the reference dies with at :1448
+        if h_needed[k] and states[k] == 2:
+            raise IndexError("stale M_M_sub window of another resolution is too small for resolution %d (:1448)" % res)
+
+
 # ======================================================================================
 # (c) two-step allelic correction
 # ======================================================================================

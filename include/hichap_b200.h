@@ -92,6 +92,26 @@ int hc_bin_band_finish(int32_t* mats, const int64_t* mat_off, const int32_t* mat
                        const int64_t* bin_off, int32_t nchrom, const int32_t* h_mat_n, int32_t band_width,
                        void* work, void* stream);
 
+/* Inter-chromosomal imputation on the genome-wide haplotype matrix: replaces the per-line loops of
+ * matrixBuilding.py:1302-1378 (M_M file, own_is_p = 0) and :1416-1492 (P_P file, own_is_p = 1), bug for
+ * bug.  Only lines with mark != Both and c1 != c2 act.  `un` (total x total, leading dimension ld) is the
+ * UN-imputed matrix the vote reads; `imp` receives the +1s.  start_m / start_p: device int64[nchrom]
+ * first bins of the maternal / paternal copy of each chromosome.  half_width = Imputation_region // res;
+ * nb_i / nb_j: device int32[npts] window indices of GetNeighborhoodIndex (:721-732).
+ * last_qualifying (nullable, device, initialised to -1 by the caller): atomic max of the index of lines
+ * that passed the window bounds checks -- for the M_M file it identifies the window the reference
+ * leaves in `M_M_sub`, which its P_P R1 branch then reads (:1448).  For the P_P file the caller passes
+ * that window's disc sum in stale_sum (stale_state 0), or stale_state 1 / 2 when the reference would
+ * raise NameError / IndexError at the first such line; *stale_needed (device int32, zeroed by the caller)
+ * is then set if one exists. */
+int hc_impute_inter(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                    const uint8_t* mark, int64_t npairs, int32_t res, const int64_t* start_m,
+                    const int64_t* start_p, int32_t nchrom, int32_t own_is_p, const int32_t* un,
+                    int32_t* imp, int32_t total, int64_t ld, int32_t half_width, const int32_t* nb_i,
+                    const int32_t* nb_j, int32_t npts, int64_t imputation_min, double imputation_ratio,
+                    int32_t stale_state, int64_t stale_sum, long long* last_qualifying,
+                    int32_t* stale_needed, void* stream);
+
 /* Chromosome-id columns may cross PCIe as uint8 (255 = filtered chromosome): widen to the int32
  * columns the binning entry points take (255 -> -1). */
 int hc_widen_u8_i32(const uint8_t* src, int32_t* dst, int64_t n, void* stream);

@@ -59,7 +59,8 @@ class _FakePopen:
         return "", ""
 
 
-def run_reference_haplotype(bed_dir, genome_size, whole_res, local_res, chroms, out_dir):
+def run_reference_haplotype(bed_dir, genome_size, whole_res, local_res, chroms, out_dir,
+                            imputation=(10000000, 2, 0.9)):
     """Execute the reference's HaplotypeMatrixBuilding with I/O side effects stubbed."""
     mod = ref_shim.load()
     saved = (mod.subprocess, mod.NPZ2Cooler)
@@ -68,7 +69,7 @@ def run_reference_haplotype(bed_dir, genome_size, whole_res, local_res, chroms, 
     mod.NPZ2Cooler = lambda **kw: calls.append(kw)
     try:
         prefix, datasets = mod.HaplotypeMatrixBuilding(out_dir, bed_dir, genome_size, whole_res, local_res,
-                                                       10000000, 2, 0.9, chroms)
+                                                       imputation[0], imputation[1], imputation[2], chroms)
     finally:
         mod.subprocess, mod.NPZ2Cooler = saved
     return prefix, datasets, calls
@@ -122,6 +123,46 @@ def write_allelic_beds(td, names, c1, p1, c2, p2, cls, mark):
         with open(os.path.join(bed_dir, "S_Valid_%s.bed" % tag), "w") as fh:
             fh.writelines(synth.allelic_lines(names, c1[sel], p1[sel], c2[sel], p2[sel], mk))
     return bed_dir
+
+
+def imputation_inputs(seed=33, n=60000):
+    """Allelic beds with many inter-chromosomal contacts, so that the neighbourhood vote of the
+    imputation (matrixBuilding.py:1302-1378, :1416-1492) fires in every branch."""
+    rng = np.random.default_rng(seed)
+    names, c1, p1, c2, p2 = small_pairs(n, seed=seed, trans_frac=0.45)
+    cls = rng.choice(5, size=n, p=[0.20, 0.32, 0.32, 0.08, 0.08])
+    mark = rng.choice(3, size=n, p=[0.4, 0.3, 0.3]).astype(np.uint8)
+    return names, c1, p1, c2, p2, cls, mark
+
+
+IMPUTATION_CASES = [      # (wholeRes in call order, Imputation_region, Imputation_min, Imputation_ratio)
+    ([500000, 250000], 1500000, 2, 0.6),
+    ([500000], 1000000, 1, 0.9),
+    ([250000], 2500000, 3, 0.55),
+]
+
+
+def make_imputation():
+    """imputation_small.npz: genome-wide un-imputed / imputed haplotype matrices of the reference's
+    HaplotypeMatrixBuilding for several (wholeRes, region, min, ratio) settings on one set of beds."""
+    names, c1, p1, c2, p2, cls, mark = imputation_inputs()
+    out = dict(names=np.array(names), c1=c1, p1=p1, c2=c2, p2=p2, cls=cls, mark=mark, ncases=np.array(len(IMPUTATION_CASES)))
+    with tempfile.TemporaryDirectory() as td:
+        gs = synth.write_genome_size(os.path.join(td, "genomeSize"), SMALL_GENOME)
+        bed_dir = write_allelic_beds(td, names, c1, p1, c2, p2, cls, mark)
+        for k, (whole_res, region, imin, ratio) in enumerate(IMPUTATION_CASES):
+            out_dir = os.path.join(td, "out%d" % k)
+            os.makedirs(out_dir)
+            _, ds, _ = run_reference_haplotype(bed_dir, gs, whole_res, [1000000], CHROMS, out_dir,
+                                               imputation=(region, imin, ratio))
+            out["case%d|params" % k] = np.array([region, imin, ratio], dtype=np.float64)
+            out["case%d|whole_res" % k] = np.array(whole_res)
+            for res in whole_res:
+                un, imp = ds["UnImputated_Whole"][res]["Matrix"], ds["Imputated_Whole"][res]["Matrix"]
+                out["case%d|un|%d" % (k, res)] = un.astype(np.int32)
+                out["case%d|imp|%d" % (k, res)] = imp.astype(np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "imputation_small.npz"), **out)
+    return out
 
 
 def make_allelic():
@@ -229,6 +270,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     trad = make_traditional()
     make_allelic()
+    make_imputation()
     make_twostep_cases()
     make_ice_restated(trad)
     for f in sorted(os.listdir(GOLDEN)):

@@ -171,3 +171,40 @@ def test_ice_edge_cases():
     x, y = np.nonzero(np.triu(M))
     w2, _ = cooler_ice.balance(x, y, M[x, y], 40, [0, 40], mad_max=0, min_nnz=0)
     assert np.array_equal(w1, w2)
+
+
+def _imputation_case(g, k, genome):
+    """Inputs of the oracle's imputation for case k of imputation_small.npz."""
+    order, c1, p1, c2, p2, cls, mark, keep = _allelic_columns(g, genome)
+    region, imin, ratio = g["case%d|params" % k]
+    whole_res = [int(r) for r in g["case%d|whole_res" % k]]
+    files = {}
+    for tag, kcls in (("M_M", 1), ("P_P", 2)):
+        sel = cls == kcls                          # file order; filtered chromosomes stay as -1
+        files[tag] = (c1[sel], p1[sel], c2[sel], p2[sel], mark[sel])
+    starts = {}
+    for res in whole_res:
+        hb, _ = ho.chro_bins_haplotypes(genome, res)
+        starts[res] = (np.array([hb["M" + c][0] for c in order]), np.array([hb["P" + c][0] for c in order]))
+    return order, files, starts, whole_res, int(region), int(imin), float(ratio)
+
+
+def test_inter_chromosomal_imputation_matches_reference_golden(small_genome_file):
+    """Bug-for-bug restatement of matrixBuilding.py:1302-1378 / :1416-1492 against matrices the
+    reference itself produced (several resolutions / region / min / ratio settings)."""
+    g = load_golden("imputation_small.npz")
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    fired = 0
+    for k in range(int(g["ncases"])):
+        order, files, starts, whole_res, region, imin, ratio = _imputation_case(g, k, genome)
+        un = {res: g["case%d|un|%d" % (k, res)].astype(np.int64) for res in whole_res}
+        imp = {res: un[res].copy() for res in whole_res}
+        for res in whole_res:
+            for tag, own in (("M_M", 0), ("P_P", 1)):
+                ho.bin_whole_onesided(*files[tag], starts[res][own], res, imp[res])
+        cis_only = {res: imp[res].copy() for res in whole_res}
+        ho.impute_inter_chromosomal(un, imp, whole_res, starts, files, region, imin, ratio)
+        for res in whole_res:
+            assert np.array_equal(imp[res], g["case%d|imp|%d" % (k, res)]), (k, res)
+            fired += int((imp[res] - cis_only[res]).sum())
+    assert fired > 1000          # the fixtures do exercise the neighbourhood vote

@@ -62,3 +62,78 @@ def test_two_step_equals_reference(seed):
     for gap in (np.array([]), np.array([1, 5, 6, 30])):
         np.testing.assert_array_equal(ho.trans2symmetry(S, gap), mod.Trans2symmetry(S, gap))
     np.testing.assert_array_equal(ho.correct_vc(S, 2 / 3), mod.Correct_VC(S, 2 / 3))
+
+
+def test_neighborhood_index_equals_reference():
+    mod = ref_shim.load()
+    for L in list(range(0, 26)) + [40, 100]:
+        ri, rj = mod.GetNeighborhoodIndex(L)
+        oi, oj = ho.neighborhood_index(L)
+        assert list(oi) == list(ri) and list(oj) == list(rj), L
+
+
+def _live_imputation(tmp_path, seed, whole_res, params, drop_mm_onesided=False, n=20000):
+    """Run the reference's HaplotypeMatrixBuilding and the oracle's imputation on the same fresh beds."""
+    import os
+    from conftest import CHROMS
+    from oracle import make_golden as mg
+    from test_oracle_golden import _allelic_columns
+    names, c1, p1, c2, p2, cls, mark = mg.imputation_inputs(seed=seed, n=n)
+    if drop_mm_onesided:
+        mark = np.where(cls == 1, 0, mark).astype(np.uint8)       # every M_M line is 'Both'
+    gs = synth.write_genome_size(str(tmp_path / "genomeSize"), SMALL_GENOME)
+    bed_dir = mg.write_allelic_beds(str(tmp_path), names, c1, p1, c2, p2, cls, mark)
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    genome = ho.load_genome(gs, CHROMS)
+    g = dict(names=np.array(names), c1=c1, p1=p1, c2=c2, p2=p2, cls=cls, mark=mark)
+    order, k1, q1, k2, q2, cls, mark, keep = _allelic_columns(g, genome)
+    files = {tag: tuple(a[cls == k] for a in (k1, q1, k2, q2, mark)) for tag, k in (("M_M", 1), ("P_P", 2))}
+    starts = {}
+    for res in whole_res:
+        hb, _ = ho.chro_bins_haplotypes(genome, res)
+        starts[res] = (np.array([hb["M" + c][0] for c in order]), np.array([hb["P" + c][0] for c in order]))
+
+    def reference():
+        return mg.run_reference_haplotype(bed_dir, gs, whole_res, [1000000], CHROMS, out_dir, imputation=params)[1]
+
+    def oracle(ds):
+        un = {res: ds["UnImputated_Whole"][res]["Matrix"].astype(np.int64) for res in whole_res}
+        imp = {res: un[res].copy() for res in whole_res}
+        for res in whole_res:
+            for tag, own in (("M_M", 0), ("P_P", 1)):
+                ho.bin_whole_onesided(*files[tag], starts[res][own], res, imp[res])
+        return ho.impute_inter_chromosomal(un, imp, whole_res, starts, files, *params)
+    return reference, oracle
+
+
+@pytest.mark.parametrize("seed,whole_res,params", [(201, [500000], (1500000, 2, 0.7)),
+                                                    (202, [1000000, 250000], (2000000, 1, 0.5)),
+                                                    (203, [250000], (750000, 2, 0.95))])
+def test_imputation_equals_reference_live(tmp_path, seed, whole_res, params):
+    reference, oracle = _live_imputation(tmp_path, seed, whole_res, params)
+    ds = reference()
+    imp = oracle(ds)
+    for res in whole_res:
+        assert np.array_equal(imp[res], ds["Imputated_Whole"][res]["Matrix"]), res
+
+
+def test_imputation_error_behaviour_equals_reference(tmp_path):
+    """The reference dies with NameError when its P_P loop needs `M_M_sub` and the M_M loop never set it,
+    and with IndexError when the stale window belongs to a coarser resolution."""
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    reference, oracle = _live_imputation(tmp_path / "a", 204, [500000], (1500000, 2, 0.7), drop_mm_onesided=True)
+    with pytest.raises(NameError):
+        reference()
+    # the oracle raises the same way on the same inputs (un-imputed matrices do not matter for the error)
+    zeros = {"UnImputated_Whole": {500000: {"Matrix": np.zeros((82, 82), np.int64)}}}
+    with pytest.raises(NameError):
+        oracle(zeros)
+    reference, oracle = _live_imputation(tmp_path / "b", 205, [250000, 500000], (1500000, 2, 0.7))
+    with pytest.raises(IndexError):
+        reference()
+    zeros = {"UnImputated_Whole": {250000: {"Matrix": np.zeros((160, 160), np.int64)},
+                                   500000: {"Matrix": np.zeros((82, 82), np.int64)}}}
+    with pytest.raises(IndexError):
+        oracle(zeros)
