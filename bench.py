@@ -170,8 +170,15 @@ def run_ours(args):
     launches = (_abi.launch_count() - launches0) // args.steps
     # roofline of the dominant kernel (the fused ICE iteration), from the same timed steps
     iters = out["results"]["iters"].astype(np.int64)
-    ice_bytes = float(sum(int(it) * 4 * n * n for it, n in zip(iters, sizes)))
-    loop_ms = float(out["info"].loop_ms)
+    info = out["info"]
+    packed = bool(info.packed)
+    # algorithmic bytes of the stream kernel: the matrix once per iteration -- 4 B per cell as int32 tiles, or
+    # (packed encoding, default) 1 B per cell + 8 B per overflow cell (col, extra count)
+    cell_iters = float(sum(int(it) * n * n for it, n in zip(iters, sizes)))
+    mean_iters = cell_iters / max(float(sum(n * n for n in sizes)), 1.0)
+    ice_bytes = (1.0 * cell_iters + 8.0 * float(info.overflow_cells) * mean_iters) if packed else 4.0 * cell_iters
+    ice_kernel = "ice_q8_mma_kernel" if packed else "ice_dense_stream_kernel"
+    loop_ms = float(info.loop_ms)
     n_iter_launches = int(max(iters))   # stream-kernel launches that had work (graph replays run in chunks of 8)
 
     # ---- end to end through the host-facing call ---------------------------------------------
@@ -179,7 +186,8 @@ def run_ours(args):
         if rank == 0:
             sampler.stop()
             print(json.dumps({"tuning_only": True, "ms_per_step": ms_step, "ice_loop_ms": loop_ms,
-                              "ice_GBps": ice_bytes / (loop_ms * 1e6), "ice_launches": n_iter_launches,
+                              "ice_GBps": ice_bytes / (loop_ms * 1e6), "ice_launches": n_iter_launches, "ice_kernel": ice_kernel,
+                              "pack_ms": float(info.pack_ms), "overflow_cells": int(info.overflow_cells), "iters_max": int(max(iters)),
                               "variant": os.environ.get("HC_ICE_VARIANT"), "item_kb": os.environ.get("HC_ICE_ITEM_KB")}))
         if world > 1:
             dist.destroy_process_group()
@@ -236,9 +244,11 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one full launch, from the committed ncu capture
     try:
-        traffic = float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["traffic_bytes_per_launch"]) if world == 1 else None
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = float(tj["traffic_bytes_per_launch"]) if world == 1 and str(tj.get("kernel", "ice_dense_stream_kernel")).startswith(ice_kernel) else None
+        traffic_note = tj.get("note", "")
     except Exception:
-        traffic = None
+        traffic, traffic_note = None, ""
     achieved = ice_bytes / (loop_ms * 1e6) if loop_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -255,14 +265,14 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h.item()), "steps": e2e_steps,
                 "Mpairs_per_s": args.pairs / (ms_e2e * 1e3)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "ice_dense_stream_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": ice_kernel, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_launch": ice_bytes / max(n_iter_launches, 1),
                      "launches": n_iter_launches, "avg_launch_ms": loop_ms / max(n_iter_launches, 1),
-                     "traffic": traffic,
-                     "traffic_note": "ncu --set full capture of a launch with all 23 chromosomes active (profiles/ncu_traffic.json); "
-                                     "algorithmic bytes of that launch = sum 4*N^2 = 1.183e9 (1.205e9 with the 128-column row padding)"},
+                     "encoding": ("uint8 cells + overflow list, built once per call in %.3f ms (%d overflow cells)"
+                                  % (float(info.pack_ms), int(info.overflow_cells))) if packed else "int32 tiles",
+                     "traffic": traffic, "traffic_note": traffic_note},
         "breakdown": breakdown, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

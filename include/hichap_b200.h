@@ -195,6 +195,9 @@ typedef struct hc_ice_result {
 typedef struct hc_ice_run_info {
     int32_t launches; /* kernels launched by the call (iterations + finalise)                  */
     float loop_ms;    /* device time of the iteration loop (CUDA events on `stream`)           */
+    int32_t packed;   /* dense: 1 when the loop streamed the uint8 + overflow encoding         */
+    float pack_ms;    /* dense: device time of building that encoding (once per call)          */
+    int64_t overflow_cells; /* dense, packed: cells whose weighted count exceeds 255           */
 } hc_ice_run_info;
 
 /* Iterate every problem of the dense batch to convergence, independently (own loop, scale and
@@ -202,8 +205,10 @@ typedef struct hc_ice_run_info {
  * bias: in = initial bias from the filters, out = final weights (NaN for masked bins, divided
  * by sqrt(scale) when rescale_marginals).  work: 3*nbins doubles.  The reduction over the
  * marginals, the bias update, the rescale and the convergence test all run on the device
- * inside the same kernel that streams the matrix; the host only polls a done counter.
- * Every mat_ld must be a multiple of 128 elements (512-byte rows). */
+ * (stream kernel + per-chromosome update kernel, replayed as a CUDA graph); the host only polls a
+ * done counter.  By default the tiles are first re-encoded into uint8 + an overflow list (exact; a
+ * quarter of the bytes per iteration; HC_ICE_PACKED=0 streams the int32 tiles instead) in stream-ordered
+ * scratch of 1 byte per tile element.  Every mat_ld must be a multiple of 128 elements (512-byte rows). */
 int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
                          const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
                          const int32_t* h_mat_n, const hc_ice_params* h_params, double* bias,
