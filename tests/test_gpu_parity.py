@@ -260,6 +260,65 @@ def test_ice_chr21_sized_vs_oracle(mb, cuda_device):
     assert abs(m.mean() - 1) < 1e-3 and m.var() < 1e-4
 
 
+def _ice_matrix(n, seed, scale=30.0, heavy_diag=False):
+    rng = np.random.default_rng(seed)
+    bias = np.exp(rng.normal(0, 0.4, n))
+    d = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) + 1.0
+    M = rng.poisson(scale * bias[:, None] * bias[None, :] / d)
+    if heavy_diag:                      # counts far above 255 next to the diagonal: the overflow list of the packed encoding
+        M = M + rng.poisson(3000.0 / d ** 2)
+    M = np.triu(M) + np.triu(M, 1).T
+    M[n // 3:n // 3 + 5, :] = 0; M[:, n // 3:n // 3 + 5] = 0
+    return M
+
+
+def _ice_vs_oracle(mb, mats, what, **kw):
+    w, st = mb.ice_balance_dense(mats, **kw)
+    off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])])
+    b1, b2, cnt = [], [], []
+    for m, lo in zip(mats, off[:-1]):
+        x, y = np.nonzero(np.triu(m)); b1.append(x + lo); b2.append(y + lo); cnt.append(m[x, y])
+    b1, b2, cnt = (np.concatenate(v) for v in (b1, b2, cnt))
+    ref, rst = cooler_ice.balance(b1, b2, cnt, int(off[-1]), off, cis_only=True, **kw)
+    check_weights(w, ref, what)
+    assert st["iters"] == rst["iters"], what
+    assert st["converged_per_chrom"] == rst["converged_per_chrom"], what
+
+
+@pytest.mark.parametrize("env,sizes,kw", [
+    ({}, (700, 333), dict()),                                        # packed encoding, cluster update kernel
+    ({}, (700, 333), dict(ignore_diags=0)),                          # kept diagonal counts twice: values up to 2 x count
+    ({"HC_ICE_KSEG": "4"}, (1500,), dict()),                         # 12 K-segments per row: more than the unrolled 8
+    ({"HC_ICE_KSEG": "8", "HC_ICE_Q8_VARIANT": "0"}, (900, 40), dict()),   # two strips per work item
+    ({"HC_ICE_CLUSTER_UPDATE": "0"}, (700, 333), dict()),            # single-CTA update kernel on the packed encoding
+    ({"HC_ICE_PACKED": "0"}, (700, 333), dict()),                    # int32 tiles, fp64 FMA kernel
+])
+def test_ice_encodings_and_kernel_variants(mb, monkeypatch, env, sizes, kw):
+    """Every stream / update kernel variant of hc_ice_dense_balance against the oracle, with counts far above 255
+    (overflow cells of the packed encoding) and masked rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    mats = [_ice_matrix(n, 40 + i, heavy_diag=True) for i, n in enumerate(sizes)]
+    assert max(int(m.max()) for m in mats) > 1000
+    _ice_vs_oracle(mb, mats, "variant %r %r" % (env, kw), **kw)
+
+
+def test_ice_more_than_8192_columns(mb):
+    """A matrix wider than the cluster update kernel covers (8 x 256 x 4 columns): generic update path on the
+    packed encoding, several K-segments."""
+    n, rng = 8300, np.random.default_rng(77)
+    bias = np.exp(rng.normal(0, 0.3, n))
+    M = np.zeros((n, n), np.int64)
+    for k in range(0, 400):                 # banded counts, built diagonal by diagonal (cheap to generate)
+        lam = (3000.0 / (k + 1) ** 2 + 40.0 / (k + 1)) * bias[:n - k] * bias[k:]
+        v = rng.poisson(lam)
+        M[np.arange(n - k), np.arange(k, n)] = v
+        M[np.arange(k, n), np.arange(n - k)] = v
+    M[2000:2010, :] = 0; M[:, 2000:2010] = 0
+    assert M.max() > 1000
+    _ice_vs_oracle(mb, [M], "n=8300", max_iters=60)
+
+
 # ---------------------------------------------------------------------------------------
 # (c) two-step correction
 # ---------------------------------------------------------------------------------------
