@@ -56,7 +56,14 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     # histogram used to agree on the row boundaries
     rows = (skeys >> col_bits)
     hist = torch.bincount(rows, minlength=nbins).to(torch.int64)
-    total = hist.clone()
+    # cut on DISTINCT keys per row (what a rank will store after reduce-by-key), not on pairs: the many duplicate
+    # pairs next to the diagonal would otherwise skew the cuts (a key held by several ranks is counted once per rank)
+    if m > 1:
+        first = torch.ones(m, dtype=torch.bool, device=dev)
+        first[1:] = skeys[1:] != skeys[:-1]
+        total = torch.bincount(rows[first], minlength=nbins).to(torch.int64)
+    else:
+        total = hist.clone()
     dist.all_reduce(total)
     cuts = row_cuts_from_counts(total.cpu().numpy(), world)
     send = exchange_plan(hist.cpu().numpy(), cuts)

@@ -60,15 +60,21 @@ def main():
         ref, rst = cooler_ice.balance(key // total, key % total, cnt, total, off, cis_only=False)
         good = ~np.isnan(ref)
         err = float(np.max(np.abs(w[good] - ref[good]) / np.abs(ref[good])))
-        ok = (np.array_equal(np.isnan(w), np.isnan(ref)) and err < 1e-6 and st["iters"] == rst["iters"] and same)
+        nan_same = np.array_equal(np.isnan(w), np.isnan(ref))
+        ok = (nan_same and err < 1e-6 and st["iters"] == rst["iters"] and bool(same))
+        if not ok:
+            bad = np.nonzero(np.isnan(w) != np.isnan(ref))[0]
+            print("DIST_CHECK detail: nan_same=%s err_ok=%s iters %r vs %r same=%r mismatching bins %s w=%s ref=%s"
+                  % (nan_same, err < 1e-6, st["iters"], rst["iters"], same, bad[:10], w[bad[:10]], ref[bad[:10]]))
         sizes = [int(x.item()) for x in allnnz]
         bal = max(sizes) / (sum(sizes) / world)
         msg = ["world=%d iters=%d (oracle %d) max_rel_err=%.2e identical_across_ranks=%s nnz/rank=%s imbalance=%.3f "
                "launches=%d loop_ms=%.2f cuts=%s" % (world, st["iters"], rst["iters"], err, same, sizes, bal,
                                                      st["launches"], st["loop_ms"], cuts)]
-        # rows are the sharding granularity: a rank may exceed the mean by at most one (dense) row
+        # the cuts balance the distinct keys each rank holds before the exchange (a proxy for the stored entries);
+        # rows are the sharding granularity: within 5 % of the mean, or at most two (dense) rows above it
         rows_nnz = np.bincount(np.concatenate([key // total, key % total]), minlength=total)
-        ok = ok and max(sizes) <= sum(sizes) / world + 2 * rows_nnz.max()
+        ok = ok and (bal <= 1.05 or max(sizes) <= sum(sizes) / world + 2 * rows_nnz.max())
         print("DIST_CHECK", "OK" if ok else "FAIL", *msg)
     kernels.nccl_comm_destroy(comm)
     dist.destroy_process_group()
