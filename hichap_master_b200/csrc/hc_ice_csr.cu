@@ -141,6 +141,7 @@ ice_csr_window_kernel(CsrView A, const double* __restrict__ bias, long long nbin
         if (threadIdx.x == 0) blk_s = atomicAdd(block_counter, 1u);
         __syncthreads();                       // also: every warp is done reading the previous window
         const long long blk = blk_s;
+        __syncthreads();                       // blk_s is rewritten by thread 0 at the top of the next round
         if (blk >= nblocks) break;
         const long long rl0 = blk * ROWS_PER_CTA, rl1 = min(rl0 + ROWS_PER_CTA, A.nloc);
         long long w0 = (A.row0 + (rl0 + rl1) / 2 - win / 2) & ~1ll;  // 16-byte aligned source

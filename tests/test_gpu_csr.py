@@ -99,7 +99,10 @@ def check_weights(w, ref, what):
     assert err < RTOL, what
 
 
-def test_ice_csr_restated_golden(K, cuda_device):
+@pytest.mark.parametrize("window", ["0", "1"])
+def test_ice_csr_restated_golden(K, cuda_device, monkeypatch, window):
+    """window=1: the opt-in stream kernel that stages a bias window with a TMA bulk copy (HC_CSR_WINDOW)."""
+    monkeypatch.setenv("HC_CSR_WINDOW", window)
     g = load_golden("ice_restated.npz")
     off = g["chrom_offsets"]
     n = int(off[-1])
