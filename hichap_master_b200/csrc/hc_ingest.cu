@@ -30,7 +30,7 @@ bool map_file(const char* path, Mapped* m) {
     if (fstat(m->fd, &st) != 0) { close(m->fd); return false; }
     m->n = (size_t)st.st_size;
     if (m->n == 0) { m->p = nullptr; return true; }
-    void* a = mmap(nullptr, m->n, PROT_READ, MAP_PRIVATE, m->fd, 0);
+    void* a = mmap(nullptr, m->n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, m->fd, 0);
     if (a == MAP_FAILED) { close(m->fd); return false; }
     madvise(a, m->n, MADV_SEQUENTIAL);
     m->p = (const char*)a;
@@ -41,7 +41,13 @@ void unmap_file(Mapped* m) {
     if (m->fd >= 0) close(m->fd);
 }
 
-inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+// whitespace as str.split() sees it inside a line ('\n' never occurs inside one)
+struct WsTable {
+    bool t[256];
+    WsTable() { for (int i = 0; i < 256; ++i) t[i] = i == ' ' || i == '\t' || i == '\r' || i == '\f' || i == '\v'; }
+};
+const WsTable g_ws;
+inline bool is_ws(char c) { return g_ws.t[(unsigned char)c]; }
 
 struct ChromTable {
     std::unordered_map<std::string, int> id;   // stripped name -> index into the sorted chromosome table
@@ -123,19 +129,30 @@ void parse_chunk(const char* b, const char* e, int layout, const ChromTable& T, 
     while (b < e) {
         const char* nl = (const char*)memchr(b, '\n', (size_t)(e - b));
         const char* le = nl ? nl : e;
-        // split on runs of whitespace, keep the first 14 fields and remember the last one
+        // split on runs of whitespace: only the first `need` fields are located one by one (the valid-pair layout
+        // uses fields 1, 6, 8, 13 of 23); the last field (the allelic mark) is found from the end of the line
+        const int need = layout == 0 ? 14 : 4;
         int nf = 0;
         const char* last_s = nullptr; size_t last_n = 0;
         const char* p = b;
-        while (p < le) {
+        while (p < le && nf < need) {
             while (p < le && is_ws(*p)) ++p;
             if (p >= le) break;
             const char* q = p;
             while (q < le && !is_ws(*q)) ++q;
-            if (nf < 24) { fs[nf] = p; fl[nf] = (size_t)(q - p); }
+            fs[nf] = p; fl[nf] = (size_t)(q - p);
             last_s = p; last_n = (size_t)(q - p);
             ++nf;
             p = q;
+        }
+        if (layout != 0 && nf == need) {          // line[-1]: the last whitespace-separated token of the line
+            const char* r = le;
+            while (r > p && is_ws(r[-1])) --r;
+            if (r > p) {                          // there is something after field 3
+                const char* l = r;
+                while (l > p && !is_ws(l[-1])) --l;
+                last_s = l; last_n = (size_t)(r - l);
+            }
         }
         b = nl ? nl + 1 : e;
         if (nf == 0) continue;    // blank line
@@ -175,6 +192,7 @@ struct ParseJob {
     std::vector<std::pair<const char*, const char*>> chunks;
     std::vector<ChunkOut> outs;
     int layout = 0;
+    int nthreads = 0;
 };
 
 thread_local ParseJob* g_job = nullptr;   // result of the last hc_ingest_parse on this thread
@@ -213,6 +231,7 @@ extern "C" int hc_ingest_parse(const char* const* paths, int32_t npaths, int32_t
     }
     if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
     if (nthreads <= 0) nthreads = 1;
+    J.nthreads = nthreads;
     const size_t target = 8u << 20;   // ~8 MB newline-aligned chunks, in file order
     for (auto& f : J.files) {
         const char* b = f.p;
@@ -256,16 +275,31 @@ extern "C" int hc_ingest_parse(const char* const* paths, int32_t npaths, int32_t
 // Copy the parsed columns into caller buffers (npairs entries each; mark may be NULL) and free them.
 extern "C" int hc_ingest_fetch(int32_t* c1, int32_t* p1, int32_t* c2, int32_t* p2, uint8_t* mark) {
     HC_REQUIRE(g_job != nullptr, "no parsed data on this thread");
-    size_t off = 0;
-    for (auto& o : g_job->outs) {
-        const size_t n = o.c1.size();
-        if (n) {
-            memcpy(c1 + off, o.c1.data(), n * 4); memcpy(p1 + off, o.p1.data(), n * 4);
-            memcpy(c2 + off, o.c2.data(), n * 4); memcpy(p2 + off, o.p2.data(), n * 4);
-            if (mark && g_job->layout != 0) memcpy(mark + off, o.mark.data(), n);
+    ParseJob& J = *g_job;
+    std::vector<size_t> off(J.outs.size() + 1, 0);
+    for (size_t i = 0; i < J.outs.size(); ++i) off[i + 1] = off[i] + J.outs[i].c1.size();
+    const bool want_mark = mark != nullptr && J.layout != 0;
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {       // chunk-parallel: the destination pages are touched for the first time here
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= J.outs.size()) break;
+            ChunkOut& o = J.outs[i];
+            const size_t n = o.c1.size();
+            if (n) {
+                memcpy(c1 + off[i], o.c1.data(), n * 4); memcpy(p1 + off[i], o.p1.data(), n * 4);
+                memcpy(c2 + off[i], o.c2.data(), n * 4); memcpy(p2 + off[i], o.p2.data(), n * 4);
+                if (want_mark) memcpy(mark + off[i], o.mark.data(), n);
+            }
+            ChunkOut().c1.swap(o.c1); ChunkOut().p1.swap(o.p1); ChunkOut().c2.swap(o.c2); ChunkOut().p2.swap(o.p2);
         }
-        off += n;
-    }
+    };
+    int nt = J.nthreads > 0 ? J.nthreads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::min<size_t>((size_t)std::max(nt, 1), std::max<size_t>(J.outs.size(), 1));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
     delete g_job;
     g_job = nullptr;
     return HC_OK;

@@ -136,3 +136,22 @@ def test_native_parser_errors_and_edge_cases(tmp_path, small_genome_file):
         pairs.read_pair_files([str(junk)], order, CHROMS, "allelic")
     with pytest.raises(IOError):
         pairs.read_pair_files([str(tmp_path / "missing.bed")], order, CHROMS, "allelic")
+
+
+def test_native_parser_whitespace_and_last_token(tmp_path):
+    """str.split() semantics: runs of blanks / tabs, leading blanks, trailing blanks, blank lines; the allelic mark
+    is the LAST token of the line (matrixBuilding.py:1270 `line[-1]`), which for a 4-column line is the position."""
+    from hichap_master_b200 import pairs
+    order = ["1", "2", "X"]
+    text = ("chr1\t100\tchr2\t200\tBoth\nchr1 300   chrX\t400\nchr2\t5\tchr2\t6\tR1  \n\n"
+            "  chrX\t7\tchr1\t8\tfoo bar\tR2\nchrM\t1\tchr1\t2\tBoth\n")
+    path = tmp_path / "a.bed"
+    path.write_text(text)
+    c1, p1, c2, p2, mark = pairs.read_pair_files([str(path)], order, ["#", "X"], "allelic")
+    assert c1.tolist() == [0, 0, 1, 2] and p1.tolist() == [100, 300, 5, 7]
+    assert c2.tolist() == [1, 2, 1, 0] and p2.tolist() == [200, 400, 6, 8]
+    assert mark.tolist() == [0, 3, 1, 2]
+    # same lines through the stream parser (pandas) used for file-like inputs
+    import io
+    d1, q1, d2, q2, mk = pairs.read_pairs(io.StringIO("chr1\t100\tchr2\t200\tBoth\nchr2\t5\tchr2\t6\tR1\n"), order, ["#", "X"], "allelic")
+    assert d1.tolist() == [0, 1] and mk.tolist() == [0, 1]
