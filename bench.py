@@ -253,7 +253,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "int32 counts / f64 weights", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": "int32 counts (ICE streams them as u8 + overflow list, s32 tensor-core plane sums) / f64 weights" if packed else "int32 counts / f64 weights",
+        "data": "synthetic",
         "config": {"workload": workload_name(args.pairs), "pairs": args.pairs, "bins": int(sum(sizes_all)),
                    "resolution": RES, "chromosomes": len(order),
                    "parallelism": "chromosomes LPT-sharded by N^2 over %d GPU(s), no collective" % world,
