@@ -868,6 +868,24 @@ ice_finalize_kernel(const int64_t* __restrict__ bin_off, const int64_t* __restri
     bias[g] = b;
 }
 
+// stream-ordered scratch and timing events of one balancing call, released on every exit path
+struct Scratch {
+    cudaStream_t s;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(void** p, size_t bytes) {
+        const cudaError_t e = cudaMallocAsync(p, bytes, s);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, s); }
+};
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void create() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 typedef void (*StreamKernel)(IceDenseArgs);
 struct StreamVariant { StreamKernel fn; int rg, u, minb; };
 // tuned on B200 (profiles/): RG rows share the bias loads; RG*U 128-bit loads in flight per lane
@@ -1075,8 +1093,9 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         for (int p : order) { desc_lo[p] = run; run += cnt[p]; desc_hi[p] = run; }
     }
 
+    Scratch scratch(s);
     double* d_vec = nullptr;     // [npad] bias | [npad] marg | [nprob+1] pad_off (as int64)
-    HC_CUDA(cudaMallocAsync((void**)&d_vec, (2 * (size_t)npad + nprob + 1) * sizeof(double), s));
+    HC_CUDA(scratch.alloc((void**)&d_vec, (2 * (size_t)npad + nprob + 1) * sizeof(double)));
     double* biasp = d_vec;
     double* marg = d_vec + npad;
     int64_t* d_pad = reinterpret_cast<int64_t*>(d_vec + 2 * npad);
@@ -1094,9 +1113,11 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     int64_t* d_qoff = nullptr;
     int32_t* d_exp = nullptr;
     long long novf = 0;
-    cudaEvent_t evp0 = nullptr, evp1 = nullptr;
+    EventPair evp;
+    cudaEvent_t& evp0 = evp.a;
+    cudaEvent_t& evp1 = evp.b;
     if (packed) {
-        if (h_info) { cudaEventCreate(&evp0); cudaEventCreate(&evp1); cudaEventRecord(evp0, s); }
+        if (h_info) { evp.create(); cudaEventRecord(evp0, s); }
         std::vector<int64_t> h_q(2 * (size_t)nprob + 1);     // q_off[nprob] | strip_off[nprob+1]
         int64_t qbytes = 0, strips = 0;
         for (int p = 0; p < nprob; ++p) {
@@ -1107,11 +1128,11 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
             strips += sp;
         }
         h_q[2 * (size_t)nprob] = strips;
-        HC_CUDA(cudaMallocAsync((void**)&d_q8, (size_t)qbytes + 8 * (size_t)npad * (1 + (size_t)nseg_max) + 16, s));
+        HC_CUDA(scratch.alloc((void**)&d_q8, (size_t)qbytes + 8 * (size_t)npad * (1 + (size_t)nseg_max) + 16));
         d_digits = d_q8 + ((qbytes + 15) & ~15ll);
         d_part = reinterpret_cast<double*>(d_digits + 8 * (size_t)npad);
         const size_t ptr_bytes = ((size_t)nbins + 1 + 2 * (size_t)nprob + 1 + (size_t)((nbins + 1023) / 1024) + 1) * sizeof(int64_t);
-        HC_CUDA(cudaMallocAsync((void**)&d_ovf_ptr, ptr_bytes + (2 * (size_t)nbins + nprob) * sizeof(int32_t), s));
+        HC_CUDA(scratch.alloc((void**)&d_ovf_ptr, ptr_bytes + (2 * (size_t)nbins + nprob) * sizeof(int32_t)));
         d_qoff = d_ovf_ptr + nbins + 1;
         int64_t* d_strip = d_qoff + nprob;
         int32_t* d_lo = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_ovf_ptr) + ptr_bytes);
@@ -1139,7 +1160,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
             HC_LAUNCH_CHECK();
         }
         HC_CUDA(hc_read_small(&novf, d_ovf_ptr + nbins, sizeof(long long), s));
-        HC_CUDA(cudaMallocAsync((void**)&d_ovf, 2 * (size_t)std::max(novf, 1ll) * sizeof(int32_t), s));
+        HC_CUDA(scratch.alloc((void**)&d_ovf, 2 * (size_t)std::max(novf, 1ll) * sizeof(int32_t)));
         if (novf > 0) {
             ice_pack_ovf_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, s>>>(
                 mats, mat_off, mat_n, mat_ld, bin_off, nprob, P->ignore_diags, d_ovf_ptr, d_lo, d_hi, d_ovf, d_ovf + novf);
@@ -1149,7 +1170,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     int32_t* d_tab = nullptr;    // 3 item tables | done[nprob] | n_done | queue | iter | nitems | pad to 16 B | item descriptors (packed)
     const size_t desc_at = (3 * max_items + (size_t)nprob + 4 + 3) & ~(size_t)3;
     const size_t tab_ints = desc_at + (packed ? 16 * max_items : 0);
-    HC_CUDA(cudaMallocAsync((void**)&d_tab, tab_ints * sizeof(int32_t), s));
+    HC_CUDA(scratch.alloc((void**)&d_tab, tab_ints * sizeof(int32_t)));
     bool desc_uploaded = false;
     auto upload_items = [&]() -> cudaError_t {
         const size_t n = item_prob.size();
@@ -1231,8 +1252,10 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess) { gexec = nullptr; (void)cudaGetLastError(); }   // plain launches below
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the iteration loop, for the roofline
-    if (h_info) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, s); }
+    EventPair evl;                              // device time of the iteration loop, for the roofline
+    cudaEvent_t& ev0 = evl.a;
+    cudaEvent_t& ev1 = evl.b;
+    if (h_info) { evl.create(); cudaEventRecord(ev0, s); }
     for (int k0 = 0; k0 < P->max_iters; k0 += poll) {
         cudaError_t e = cudaSuccess;
         if (gexec) e = cudaGraphLaunch(gexec, s);
@@ -1262,21 +1285,14 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; }
     }
-    cudaFreeAsync(d_tab, s);
-    cudaFreeAsync(d_vec, s);
-    if (d_q8) cudaFreeAsync(d_q8, s);
-    if (d_ovf_ptr) cudaFreeAsync(d_ovf_ptr, s);
-    if (d_ovf) cudaFreeAsync(d_ovf, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (rc == HC_OK && e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; }
     if (h_info) {
         h_info->launches = launches;
         if (ev0 && e == cudaSuccess) cudaEventElapsedTime(&h_info->loop_ms, ev0, ev1);
-        if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
         h_info->packed = packed ? 1 : 0;
         h_info->overflow_cells = novf;
         if (evp0 && e == cudaSuccess) cudaEventElapsedTime(&h_info->pack_ms, evp0, evp1);
     }
-    if (evp0) { cudaEventDestroy(evp0); cudaEventDestroy(evp1); }
     return rc;
 }
