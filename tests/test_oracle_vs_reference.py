@@ -137,3 +137,34 @@ def test_imputation_error_behaviour_equals_reference(tmp_path):
                                    500000: {"Matrix": np.zeros((82, 82), np.int64)}}}
     with pytest.raises(IndexError):
         oracle(zeros)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_genome_wide_and_intra_correction_equal_reference_live(seed, small_genome_file):
+    """GenomeWideMatrixCorrection (:857-901) and IntraChromMatrixCorrection (:1026-1041) on fresh random matrices."""
+    from conftest import CHROMS
+    mod = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    res = 500000
+    bins, total = mod.Get_Chro_Bins(small_genome_file, res, CHROMS)
+    hbins, htotal = mod.Get_Chro_Bins_Haplotypes(small_genome_file, res, CHROMS)
+    dens_t = np.clip(rng.gamma(2.0, 0.4, size=total), 0.05, None)
+    T = rng.poisson(40.0 * dens_t[:, None] * dens_t[None, :]); T = np.triu(T) + np.triu(T, 1).T
+    dens_h = np.clip(rng.gamma(2.0, 0.3, size=htotal), 0.02, None)
+    H = rng.poisson(6.0 * dens_h[:, None] * dens_h[None, :])          # imputed matrices are not symmetric
+    H[5, :] = 0; H[:, 5] = 0
+    ref = mod.GenomeWideMatrixCorrection(bins, hbins, T, H)
+    mine = ho.genome_wide_matrix_correction(bins, hbins, T, H)
+    np.testing.assert_allclose(mine, ref, rtol=1e-12, atol=0)
+    tra, hap = {}, {}
+    for c, (lo, hi) in bins.items():
+        tra[c] = T[lo:hi + 1, lo:hi + 1]
+        for h in "MP":
+            a, b = hbins[h + c]
+            hap[h + c] = H[a:b + 1, a:b + 1]
+    rn, rg = mod.IntraChromMatrixCorrection(tra, hap)
+    on, og = ho.intra_chrom_matrix_correction(tra, hap)
+    assert set(rn) == set(on) and set(rg) == set(og)
+    for k in rn:
+        np.testing.assert_allclose(on[k], rn[k], rtol=1e-12, atol=0)
+        assert np.array_equal(np.asarray(og[k], int), np.asarray(rg[k], int))
