@@ -51,6 +51,8 @@ def test_default_ice_stream_variant_does_not_spill():
         import pytest
         pytest.skip("no ptxas log (library built elsewhere)")
     text = open(log).read()
-    m = re.search(r"ice_dense_stream_kernelILi4ELi2ELi4E.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", text, flags=re.S)
-    assert m, "default variant not found in the ptxas log"
-    assert (int(m.group(2)), int(m.group(3))) == (0, 0), m.group(0)[-120:]
+    for name in ("ice_dense_stream_kernelILi4ELi2ELi4E",       # int32 tiles, default variant
+                 "ice_q8_mma_kernelILi1ELi16ELi2E"):           # packed encoding, default variant (16 x 128-bit loads in flight)
+        m = re.search(name + r".*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", text, flags=re.S)
+        assert m, name + " not found in the ptxas log"
+        assert (int(m.group(2)), int(m.group(3))) == (0, 0), m.group(0)[-120:]
