@@ -155,3 +155,58 @@ def test_native_parser_whitespace_and_last_token(tmp_path):
     import io
     d1, q1, d2, q2, mk = pairs.read_pairs(io.StringIO("chr1\t100\tchr2\t200\tBoth\nchr2\t5\tchr2\t6\tR1\n"), order, ["#", "X"], "allelic")
     assert d1.tolist() == [0, 1] and mk.tolist() == [0, 1]
+
+
+def test_cool_export_tables(tmp_path, small_genome_file):
+    """npz store -> (bins, pixels) as cooler.create_cooler takes them: cooler's bin table (ceil(len / res) bins,
+    last one clipped), pixels sorted by (bin1_id, bin2_id) with global ids, weights re-laid on those bins."""
+    from conftest import CHROMS
+    from hichap_master_b200 import cool_export
+    from hichap_master_b200.construction import MatrixStore
+    genome = ho.load_genome(small_genome_file, CHROMS)
+    order = ho.sort_chromosomes(genome)
+    rng = np.random.default_rng(3)
+    res = 500000
+    # local (intra-chromosomal) store with weights over HiCHap's len // res + 1 bins per chromosome
+    store = MatrixStore(str(tmp_path / "local.npz"))
+    dense = {}
+    for c in order:
+        n = genome[c] // res + 1
+        M = rng.poisson(2.0, size=(n, n)); M = np.triu(M) + np.triu(M, 1).T
+        if genome[c] % res == 0:
+            M[-1, :] = 0; M[:, -1] = 0            # HiCHap's extra bin past the chromosome end is never hit
+        dense[c] = M
+    store.add(res, {c: ho.dense_to_triu_records(dense[c]) for c in order})
+    w = rng.random(sum(genome[c] // res + 1 for c in order))
+    store.set_weight(res, w, dict(tol=1e-5, converged=True, scale=np.array([1.0, 2.0])))
+    path = store.save()
+    bins, pixels, attrs = cool_export.store_tables(np.load(path, allow_pickle=True), res, genome)
+    nb = {c: -(-genome[c] // res) for c in order}
+    assert len(bins) == sum(nb.values()) and list(bins["chrom"].unique()) == order
+    assert (bins["end"] - bins["start"]).max() == res and int(bins["end"].iloc[-1]) == genome[order[-1]]
+    assert attrs["converged"] is True and attrs["tol"] == 1e-5
+    assert pixels["count"].dtype == np.int32
+    key = pixels["bin1_id"].to_numpy() * len(bins) + pixels["bin2_id"].to_numpy()
+    assert np.all(np.diff(key) > 0) and np.all(pixels["bin1_id"] <= pixels["bin2_id"])
+    off, hoff = 0, 0
+    for c in order:
+        sel = (pixels["bin1_id"] >= off) & (pixels["bin1_id"] < off + nb[c])
+        R = np.zeros((nb[c], nb[c]), np.int64)
+        R[pixels["bin1_id"][sel] - off, pixels["bin2_id"][sel] - off] = pixels["count"][sel]
+        assert np.array_equal(R, np.triu(dense[c])[:nb[c], :nb[c]])
+        assert np.array_equal(bins["weight"].to_numpy()[off:off + nb[c]], w[hoff:hoff + nb[c]])
+        off += nb[c]; hoff += genome[c] // res + 1
+    # genome-wide store: blocks keyed 'c' and 'c1_c2', its own bin table
+    table, total = ho.chro_bins(genome, res)
+    W = rng.poisson(0.7, size=(total, total)); W = np.triu(W) + np.triu(W, 1).T
+    gw = MatrixStore(str(tmp_path / "whole.npz"))
+    gw.add(res, ho.whole_matrix_to_sparse_dict(table, W), table)
+    bins2, pix2, _ = cool_export.store_tables(np.load(gw.save(), allow_pickle=True), res, genome)
+    assert len(pix2) == int((np.triu(W) != 0).sum())
+    # the same ids as the dense matrix when no chromosome length is a multiple of the resolution
+    if all(genome[c] % res for c in genome):
+        R = np.zeros_like(W)
+        R[pix2["bin1_id"], pix2["bin2_id"]] = pix2["count"]
+        assert np.array_equal(R, np.triu(W))
+    with pytest.raises(RuntimeError):
+        cool_export.write_cool(path, small_genome_file, str(tmp_path / "x.mcool"))       # cooler is not installed here
