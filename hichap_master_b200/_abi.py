@@ -34,7 +34,7 @@ class IceResult(C.Structure):
 
 class IceRunInfo(C.Structure):
     _fields_ = [("launches", C.c_int32), ("loop_ms", C.c_float), ("packed", C.c_int32), ("pack_ms", C.c_float),
-                ("overflow_cells", C.c_int64)]
+                ("overflow_cells", C.c_int64), ("stream_full_ms", C.c_float), ("stream_full_launches", C.c_int32)]
 
 
 _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64

@@ -952,7 +952,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         HC_REQUIRE(h_mat_n[p] >= 0, "matrix side");
         nbins += h_mat_n[p];
     }
-    if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 0; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; }
+    if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 0; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; h_info->stream_full_ms = 0.f; h_info->stream_full_launches = 0; }
     if (nbins == 0) return HC_OK;
     // The iteration loop is replayed as a CUDA graph, which cannot be captured on the legacy default
     // stream: run on a private stream ordered after the caller's stream (the call synchronises
@@ -1238,12 +1238,28 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     cudaGraphExec_t gexec = nullptr;
     bool use_graph = true;
     if (const char* e = getenv("HC_ICE_GRAPH")) use_graph = atoi(e) != 0;
+    // HC_ICE_TIME_KERNEL=1 (set by bench.py): the first stream-kernel launch of every graph replay is bracketed by a pair
+    // of events, so that its duration can be read back separately from the update kernel and the launch gaps (external
+    // event-record nodes inside the graph; bracketing all 8 launches of a replay cost ~11 us per iteration)
+    struct EventList {
+        std::vector<cudaEvent_t> ev;
+        ~EventList() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+    } sev;
+    if (h_info != nullptr && getenv("HC_ICE_TIME_KERNEL") != nullptr && atoi(getenv("HC_ICE_TIME_KERNEL")) != 0) {
+        sev.ev.assign(2, nullptr);
+        for (auto& e : sev.ev) if (cudaEventCreate(&e) != cudaSuccess) { e = nullptr; }
+        for (auto& e : sev.ev) if (e == nullptr) { for (auto& x : sev.ev) { if (x) cudaEventDestroy(x); x = nullptr; } sev.ev.clear(); break; }
+    }
+    double stream_ms_sum = 0.0;
+    int stream_ms_n = 0;
     if (use_graph) {
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
             for (int i = 0; i < poll; ++i) {
+                if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[0], s, cudaEventRecordExternal);
                 V.fn<<<grid, 256, smem, s>>>(A);
+                if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[1], s, cudaEventRecordExternal);
                 launch_update();
             }
             e = cudaStreamEndCapture(s, &graph);
@@ -1260,12 +1276,20 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         cudaError_t e = cudaSuccess;
         if (gexec) e = cudaGraphLaunch(gexec, s);
         else for (int i = 0; i < poll; ++i) {
+            if (i == 0 && !sev.ev.empty()) cudaEventRecord(sev.ev[0], s);
             V.fn<<<grid, 256, smem, s>>>(A);
+            if (i == 0 && !sev.ev.empty()) cudaEventRecord(sev.ev[1], s);
             launch_update();
         }
         hc_count_launch(2 * poll);
         launches += 2 * poll;
         if (e == cudaSuccess) e = hc_read_small(&h_ndone, A.n_done, sizeof(int32_t), s);   // not a memcpy: see hc_read_small
+        if (e == cudaSuccess && h_ndone == 0 && !sev.ev.empty()) {
+            // no problem has finished yet: the bracketed launch streamed every matrix of the batch
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, sev.ev[0], sev.ev[1]) == cudaSuccess) { stream_ms_sum += ms; ++stream_ms_n; }
+            else (void)cudaGetLastError();
+        }
         if (e == cudaSuccess && h_ndone >= nonempty) break;
         if (e == cudaSuccess && h_ndone != seen_done) {
             // drop the converged chromosomes from the work list (their items would only be skipped)
@@ -1292,6 +1316,8 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         if (ev0 && e == cudaSuccess) cudaEventElapsedTime(&h_info->loop_ms, ev0, ev1);
         h_info->packed = packed ? 1 : 0;
         h_info->overflow_cells = novf;
+        h_info->stream_full_launches = stream_ms_n;
+        h_info->stream_full_ms = stream_ms_n ? (float)(stream_ms_sum / stream_ms_n) : 0.f;
         if (evp0 && e == cudaSuccess) cudaEventElapsedTime(&h_info->pack_ms, evp0, evp1);
     }
     return rc;

@@ -343,7 +343,7 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
     HC_REQUIRE(P->max_iters >= 1 && P->ignore_diags >= 0, "max_iters>=1, ignore_diags>=0");
     cudaStream_t s = (cudaStream_t)stream;
     const long long nbins = h_bin_off[nprob];
-    if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 0; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; }
+    if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 0; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; h_info->stream_full_ms = 0.f; h_info->stream_full_launches = 0; }
     if (nbins == 0) return HC_OK;
 
     double* marg = reinterpret_cast<double*>(work);

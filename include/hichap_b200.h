@@ -198,6 +198,8 @@ typedef struct hc_ice_run_info {
     int32_t packed;   /* dense: 1 when the loop streamed the uint8 + overflow encoding         */
     float pack_ms;    /* dense: device time of building that encoding (once per call)          */
     int64_t overflow_cells; /* dense, packed: cells whose weighted count exceeds 255           */
+    float stream_full_ms;   /* dense, HC_ICE_TIME_KERNEL=1: mean duration of a stream-kernel launch  */
+    int32_t stream_full_launches; /* ... over this many launches in which every problem was active */
 } hc_ice_run_info;
 
 /* Iterate every problem of the dense batch to convergence, independently (own loop, scale and

@@ -40,7 +40,7 @@ def test_struct_layout_matches_header():
     from hichap_master_b200 import _abi
     assert ctypes.sizeof(_abi.IceParams) == 40
     assert ctypes.sizeof(_abi.IceResult) == 24
-    assert ctypes.sizeof(_abi.IceRunInfo) == 24
+    assert ctypes.sizeof(_abi.IceRunInfo) == 32
 
 
 def test_default_ice_stream_variant_does_not_spill():
