@@ -64,7 +64,7 @@ SIGNATURES = {
     "hc_ice_dense_marginals": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "hc_ice_filter_bins": (C.c_int, [_P, _P, _I64, _P, _I32, C.POINTER(IceParams), _P, _P, _P]),
     "hc_ice_dense_balance": (C.c_int, [_P, _P, _P, _P, _P, _I32, C.POINTER(_I32), C.POINTER(IceParams),
-                                       _P, _P, _P, C.POINTER(IceRunInfo), _P]),
+                                       _P, _P, C.POINTER(IceRunInfo), _P]),
     "hc_rowstats_i32": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
     "hc_twostep_alpha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_twostep_work_bytes": (C.c_int64, [_I32]),
@@ -73,6 +73,11 @@ SIGNATURES = {
     "hc_twostep_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, C.POINTER(_I32), C.POINTER(_I64),
                                    C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64), _P, C.POINTER(_I64), _P, _P, _P, _P,
                                    _P, _P]),
+    "hc_rownnz_f64": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "hc_gap_rows": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "hc_trans2symmetry_f64": (C.c_int, [_P, _I64, _I32, _P, _P, _I64, _P]),
+    "hc_correct_vc_work_bytes": (C.c_int64, [_I32, _I32]),
+    "hc_correct_vc_f64": (C.c_int, [_P, _I64, _I32, _I32, C.c_double, _P, _I64, _P, _P]),
     "hc_pairs_to_keys": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hc_sort_work_bytes": (C.c_int64, [_I64]),
     "hc_sort_keys_u64": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, C.POINTER(_I32), _P]),

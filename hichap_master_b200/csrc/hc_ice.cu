@@ -315,7 +315,7 @@ ice_pack_tiles_kernel(const int32_t* __restrict__ mats, const int64_t* __restric
 __device__ __forceinline__ void ice_store_digits(const double (&bv)[4], int j4, double pow2, uint32_t* __restrict__ dw) {
     unsigned long long F[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) F[e] = bv[e] > 0.0 ? __double2ull_rz(bv[e] * pow2) : 0ull;     // pow2 = 2^(64 - E): exact scaling
+    for (int e = 0; e < 4; ++e) F[e] = bv[e] > 0.0 ? __double2ull_rn(bv[e] * pow2) : 0ull;     // pow2 = 2^(64 - E): exact scaling; b < 2^E and b has 53 bits, so the product is <= 2^64 - 2^11
     const int t = j4 >> 5, cc = j4 & 31, sub = (cc & 15) >> 2, reg = cc >> 4;
 #pragma unroll
     for (int pl = 0; pl < 8; ++pl) {
@@ -943,7 +943,7 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
 
 extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
                                     const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
-                                    const int32_t* h_mat_n, const hc_ice_params* P, double* bias, double* work,
+                                    const int32_t* h_mat_n, const hc_ice_params* P, double* bias,
                                     hc_ice_result* results, hc_ice_run_info* h_info, void* stream) {
     HC_REQUIRE(nprob > 0 && h_mat_n != nullptr && P != nullptr, "nprob>0, h_mat_n, params");
     HC_REQUIRE(P->max_iters >= 1 && P->ignore_diags >= 0, "max_iters>=1, ignore_diags>=0");
@@ -1024,7 +1024,6 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         h_pad[p + 1] = h_pad[p] + h_ld[p];
     }
     const int64_t npad = h_pad[nprob];
-    (void)work;   // scratch is allocated stream-ordered below; `work` is kept for ABI stability
 
     // ---- work items: RG-aligned row groups of ~item_kb KB, largest chromosomes first -----------
     std::vector<int32_t> h_done(nprob, 0);

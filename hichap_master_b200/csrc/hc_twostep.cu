@@ -522,3 +522,161 @@ extern "C" int hc_twostep_batch(const int32_t* tmats, const int64_t* t_off, cons
     HC_CUDA(cudaGetLastError());
     return HC_OK;
 }
+
+
+// =========================================================================================
+// Standalone building blocks with the reference's own granularity (SURVEY.md section 8b lists
+// Correct_VC(X, alpha) among the signatures to keep; TwoStepCorrection above fuses all of them).
+// These work on float64 matrices -- what the reference functions receive in TwoStepCorrection
+// (MM / alpha[:,None] is float) -- and on any rectangular shape where the reference allows one.
+// =========================================================================================
+namespace {
+
+// non-zero count per row of a float64 matrix: Coverage_M / Gap_defined (matrixBuilding.py:904-929)
+__global__ void __launch_bounds__(256)
+rownnz_f64_kernel(const double* __restrict__ M, int64_t ld, int nrows, int ncols, int32_t* __restrict__ rownnz) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const double* row = M + (int64_t)r * ld;
+    int c = 0;
+    for (int j = lane; j < ncols; j += 32) c += (row[j] != 0.0);     // NaN != 0 -> counted, as (i == 0).sum() does
+    c = warp_sum_i(c);
+    if (lane == 0) rownnz[r] = c;
+}
+
+// coverage -> gap flags -> ascending gap index list, one CTA (same code path as twostep_alpha_kernel)
+__global__ void __launch_bounds__(1024)
+gap_rows_kernel(const int32_t* __restrict__ nnz, int n, int ncols, int gap_mode, double q25, double* __restrict__ cov,
+                uint8_t* __restrict__ gf, int32_t* __restrict__ gi, int32_t* __restrict__ ngap) {
+    __shared__ HcSelectSmem sm;
+    gap_rows(nnz, n, ncols, gap_mode, q25, cov, gf, &sm);
+    compact_flags(gf, n, gi, ngap);
+}
+
+// Trans2symmetry (matrixBuilding.py:945-979) / Trans2symmetryLowRes (:770-776) on a float64 matrix:
+// 32 x 32 output tile per CTA; the mirrored input tile is read coalesced and transposed through shared memory
+__global__ void __launch_bounds__(256)
+trans2sym_f64_kernel(const double* __restrict__ S, int64_t ld, int n, const uint8_t* __restrict__ gapflag,
+                     double* __restrict__ out, int64_t ld_out) {
+    __shared__ double tb[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int rr = c0 + ty + 8 * a, cc = r0 + tx;          // tile (J, I)
+        tb[ty + 8 * a][tx] = (rr < n && cc < n) ? S[(int64_t)rr * ld + cc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = r0 + ty + 8 * a, j = c0 + tx;
+        if (i < n && j < n) {
+            const double sij = S[(int64_t)i * ld + j], sji = tb[tx][ty + 8 * a];
+            double v;
+            if (i == j) v = sij;
+            else if (gapflag == nullptr) v = sij + sji;
+            else if (gapflag[i] && gapflag[j]) v = fmax(sij, sji);
+            else v = (sij + sji) / 2.0;
+            out[(int64_t)i * ld_out + j] = v;
+        }
+    }
+}
+
+// Correct_VC (matrixBuilding.py:780-790): row sums (one warp per row, fixed order)
+__global__ void __launch_bounds__(256)
+rowsum_f64_kernel(const double* __restrict__ X, int64_t ld, int nrows, int ncols, double* __restrict__ rs) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const double* row = X + (int64_t)r * ld;
+    double s = 0.0;
+    for (int j = lane; j < ncols; j += 32) s += row[j];
+    s = warp_sum(s);
+    if (lane == 0) rs[r] = s;
+}
+// column sums: partial sums over chunks of 128 rows (coalesced across columns), then a fixed-order reduction
+constexpr int VC_ROWS = 128;
+__global__ void __launch_bounds__(256)
+colsum_partial_f64_kernel(const double* __restrict__ X, int64_t ld, int nrows, int ncols, double* __restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const int r0 = blockIdx.y * VC_ROWS, r1 = min(nrows, r0 + VC_ROWS);
+    double s = 0.0;
+    for (int r = r0; r < r1; ++r) s += X[(int64_t)r * ld + j];
+    part[(int64_t)blockIdx.y * ncols + j] = s;
+}
+// s = sum^alpha, zeros -> 1
+__global__ void __launch_bounds__(256)
+vc_pow_kernel(double* __restrict__ rs, int nrows, const double* __restrict__ part, int nchunks, int ncols,
+              double* __restrict__ cs, double alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nrows) {
+        double s = pow(rs[i], alpha);
+        if (s == 0.0) s = 1.0;
+        rs[i] = s;
+    } else if (i - nrows < ncols) {
+        const int j = i - nrows;
+        double s = 0.0;
+        for (int k = 0; k < nchunks; ++k) s += part[(int64_t)k * ncols + j];
+        s = pow(s, alpha);
+        if (s == 0.0) s = 1.0;
+        cs[j] = s;
+    }
+}
+__global__ void __launch_bounds__(256)
+vc_apply_f64_kernel(const double* __restrict__ X, int64_t ld, int nrows, int ncols, const double* __restrict__ rs,
+                    const double* __restrict__ cs, double* __restrict__ out, int64_t ld_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < ncols && i < nrows) out[(int64_t)i * ld_out + j] = X[(int64_t)i * ld + j] / (cs[j] * rs[i]);
+}
+
+}  // namespace
+
+extern "C" int hc_rownnz_f64(const double* M, int64_t ld, int32_t nrows, int32_t ncols, int32_t* rownnz, void* stream) {
+    HC_REQUIRE(nrows >= 0 && ncols >= 0 && ld >= ncols && rownnz != nullptr, "shape");
+    if (nrows == 0) return HC_OK;
+    rownnz_f64_kernel<<<(unsigned)(((int64_t)nrows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(M, ld, nrows, ncols, rownnz);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int hc_gap_rows(const int32_t* rownnz, int32_t n, int32_t ncols, int32_t gap_mode, double* coverage,
+                           uint8_t* gapflag, int32_t* gapidx, int32_t* ngap, void* stream) {
+    HC_REQUIRE(n > 0 && ncols > 0 && rownnz && coverage && gapflag && gapidx && ngap, "arguments");
+    HC_REQUIRE(gap_mode == HC_GAP_PERCENTILE || gap_mode == HC_GAP_FIXED, "gap_mode");
+    gap_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rownnz, n, ncols, gap_mode, 25.0 / 100.0, coverage, gapflag, gapidx, ngap);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int hc_trans2symmetry_f64(const double* S, int64_t ld, int32_t n, const uint8_t* gapflag, double* out,
+                                     int64_t ld_out, void* stream) {
+    HC_REQUIRE(n > 0 && ld >= n && ld_out >= n && S != nullptr && out != nullptr && S != out, "shape / aliasing");
+    const dim3 grid((n + 31) / 32, (n + 31) / 32);
+    trans2sym_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S, ld, n, gapflag, out, ld_out);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int64_t hc_correct_vc_work_bytes(int32_t nrows, int32_t ncols) {
+    const int64_t nchunks = (nrows + VC_ROWS - 1) / VC_ROWS;
+    return (int64_t)sizeof(double) * ((int64_t)nrows + ncols + nchunks * ncols + 8);
+}
+
+extern "C" int hc_correct_vc_f64(const double* X, int64_t ld, int32_t nrows, int32_t ncols, double alpha, double* out,
+                                 int64_t ld_out, void* work, void* stream) {
+    HC_REQUIRE(nrows > 0 && ncols > 0 && ld >= ncols && ld_out >= ncols && X && out && work, "arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nchunks = (nrows + VC_ROWS - 1) / VC_ROWS;
+    double* rs = reinterpret_cast<double*>(work);
+    double* cs = rs + nrows;
+    double* part = cs + ncols;
+    rowsum_f64_kernel<<<(unsigned)(((int64_t)nrows * 32 + 255) / 256), 256, 0, s>>>(X, ld, nrows, ncols, rs);
+    HC_LAUNCH_CHECK();
+    colsum_partial_f64_kernel<<<dim3((ncols + 255) / 256, nchunks), 256, 0, s>>>(X, ld, nrows, ncols, part);
+    HC_LAUNCH_CHECK();
+    vc_pow_kernel<<<(nrows + ncols + 255) / 256, 256, 0, s>>>(rs, nrows, part, nchunks, ncols, cs, alpha);
+    HC_LAUNCH_CHECK();
+    vc_apply_f64_kernel<<<dim3((ncols + 255) / 256, nrows), 256, 0, s>>>(X, ld, nrows, ncols, rs, cs, out, ld_out);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}

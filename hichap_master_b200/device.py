@@ -40,6 +40,30 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def as_int32_counts(arr) -> np.ndarray:
+    """Contact counts as a contiguous int32 array.  The tiles are int32 (cooler stores counts as int32
+    too, matrixBuilding.py:196); the reference's own matrices are int64 / float arrays holding integers.
+    Anything that is not an integer in int32 range is rejected instead of being truncated or wrapped."""
+    a = np.asarray(arr)
+    if a.dtype == np.int32:
+        return np.ascontiguousarray(a)
+    if a.dtype == np.bool_ or np.issubdtype(a.dtype, np.integer):
+        if a.size and (a.min() < -2**31 or a.max() > 2**31 - 1):
+            raise OverflowError("contact counts exceed the int32 range of the dense tiles")
+        return np.ascontiguousarray(a, dtype=np.int32)
+    if np.issubdtype(a.dtype, np.floating):
+        if a.size and not np.all(np.isfinite(a)):
+            raise TypeError("contact matrix holds NaN/inf; integer counts expected")
+        if a.size and (a.min() < -2**31 or a.max() > 2**31 - 1):
+            raise OverflowError("contact counts exceed the int32 range of the dense tiles")
+        out = a.astype(np.int32)
+        if a.size and not np.array_equal(out, a):
+            raise TypeError("contact matrix holds non-integral values; integer counts expected "
+                            "(corrected float matrices do not go through the int32 tiles)")
+        return np.ascontiguousarray(out)
+    raise TypeError("unsupported matrix dtype %s" % a.dtype)
+
+
 class DenseBatch:
     """Several zero-initialised int32 row-major matrices in ONE device buffer (the "dense
     tiles" of the binning kernel), plus the small device tables the kernels index them by."""
@@ -84,7 +108,7 @@ class DenseBatch:
         """Upload a host matrix (any integer dtype) into slot i."""
         n = self.sizes[i]
         assert arr.shape == (n, n), (arr.shape, n)
-        self.view(i)[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)))
+        self.view(i)[:, :n].copy_(torch.from_numpy(as_int32_counts(arr)))
 
     @classmethod
     def from_numpy(cls, mats, device=None):

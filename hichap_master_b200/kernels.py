@@ -33,10 +33,11 @@ def _raise_oob(oob, what):
 
 
 def bin_pairs_local(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
-                    check_bounds=True):
+                    check_bounds=True, oob=None):
     """Accumulate cis pairs into the per-chromosome matrices of ``batch`` (matrix i <->
-    chromosome index i).  matrixBuilding.py:595-603 and the allelic variants."""
-    oob = _oob_counter(batch.device)
+    chromosome index i).  matrixBuilding.py:595-603 and the allelic variants.  ``oob``: device
+    int64[1] counter of out-of-range pairs to add to (the caller checks it later)."""
+    oob = _oob_counter(batch.device) if oob is None else oob
     check(lib().hc_bin_pairs_local(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2),
                                    ptr(pairs.mark), pairs.n, int(res), int(mode), ptr(batch.buf),
                                    ptr(batch.mat_off), ptr(batch.mat_n), ptr(batch.mat_ld),
@@ -46,17 +47,17 @@ def bin_pairs_local(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.H
 
 
 def bin_pairs_local_banded(pairs: PairColumns, res: int, batch: DenseBatch, mode=_abi.HC_BIN_SYM_ALL,
-                           check_bounds=True, work=None, band_width=None):
+                           check_bounds=True, work=None, band_width=None, oob=None):
     """``bin_pairs_local`` for the symmetric modes on matrices that are symmetric on entry
     (freshly zeroed tiles): upper-triangle-only updates with an L2-resident near-diagonal band
     accumulator, band merge, mirror.  Falls back to the direct kernel outside its limits.
     Returns the work buffer (reusable)."""
     if len(batch) > 256 or mode == _abi.HC_BIN_ONESIDED or batch.nbins == 0:
-        bin_pairs_local(pairs, res, batch, mode, check_bounds)
+        bin_pairs_local(pairs, res, batch, mode, check_bounds, oob=oob)
         return work
     if band_width is None:
         band_width = int(os.environ.get("HC_BIN_BAND", "128"))
-    oob = _oob_counter(batch.device)
+    oob = _oob_counter(batch.device) if oob is None else oob
     nbytes = int(lib().hc_bin_band_work_bytes(batch.nbins, band_width))
     if work is None or work.numel() < nbytes:
         work = torch.empty(nbytes, dtype=torch.uint8, device=batch.device)
@@ -74,12 +75,12 @@ class BandedBinning:
     """begin -> accumulate(chunk) x N -> finish: banded binning fed chunk by chunk (e.g. while later
     chunks are still in flight over PCIe).  Chromosome columns may be int32 or uint8 (255 = filtered)."""
 
-    def __init__(self, batch: DenseBatch, res: int, mode=_abi.HC_BIN_SYM_ALL, work=None, band_width=None):
+    def __init__(self, batch: DenseBatch, res: int, mode=_abi.HC_BIN_SYM_ALL, work=None, band_width=None, oob=None):
         if len(batch) > 256 or mode == _abi.HC_BIN_ONESIDED:
             raise ValueError("banded binning: symmetric modes, at most 256 matrices")
         self.batch, self.res, self.mode = batch, int(res), int(mode)
         self.bw = int(os.environ.get("HC_BIN_BAND", "128")) if band_width is None else int(band_width)
-        self.oob = _oob_counter(batch.device)
+        self.oob = _oob_counter(batch.device) if oob is None else oob
         nbytes = int(lib().hc_bin_band_work_bytes(batch.nbins, self.bw))
         if work is None or work.numel() < nbytes:
             work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=batch.device)
@@ -228,12 +229,11 @@ def ice_dense_iterate(batch: DenseBatch, bias, params: IceParams):
     """Run every problem of the batch to convergence on the device; ``bias`` is updated in
     place to the final weights.  Returns (results ndarray of IceResult fields, IceRunInfo)."""
     dev, n = batch.device, batch.nbins
-    work = torch.empty(3 * max(n, 1), dtype=torch.float64, device=dev)
     res = torch.zeros(len(batch) * C.sizeof(IceResult), dtype=torch.uint8, device=dev)
     info = IceRunInfo(0, 0.0)
     check(lib().hc_ice_dense_balance(ptr(batch.buf), ptr(batch.mat_off), ptr(batch.mat_n),
                                      ptr(batch.mat_ld), ptr(batch.bin_off), len(batch), batch.h_mat_n,
-                                     C.byref(params), ptr(bias), ptr(work), ptr(res), C.byref(info),
+                                     C.byref(params), ptr(bias), ptr(res), C.byref(info),
                                      stream_ptr()), "hc_ice_dense_balance")
     rdt = np.dtype([("scale", "<f8"), ("var", "<f8"), ("iters", "<i4"), ("converged", "<i4")])
     return res.cpu().numpy().view(rdt), info
@@ -351,6 +351,14 @@ def key_col_bits(nbins: int) -> int:
     return max(1, int(nbins - 1).bit_length())
 
 
+def key_sort_bits(nbins: int) -> int:
+    """Bits the radix sort must look at so that the padding key ~0 sorts strictly after every real
+    key: 2*col_bits, plus one when nbins is a power of two -- the key of the last diagonal cell
+    (nbins-1, nbins-1) is then all ones in the low 2*col_bits bits and would tie with the padding."""
+    cb = key_col_bits(nbins)
+    return 2 * cb + (1 if int(nbins) == (1 << cb) else 0)
+
+
 def pairs_to_sorted_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
                          check_bounds=True):
     """pairs -> (row << col_bits | col) keys, both orientations, radix-sorted; padding keys
@@ -366,7 +374,7 @@ def pairs_to_sorted_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins:
     if check_bounds:
         _raise_oob(oob, "genome-wide")
     keys = keys[:2 * pairs.n]
-    skeys, free = sort_keys_u64(keys, 2 * col_bits) if pairs.n else (keys, None)
+    skeys, free = sort_keys_u64(keys, key_sort_bits(nbins)) if pairs.n else (keys, None)
     return skeys, free, n_valid
 
 
@@ -385,9 +393,9 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
     if check_bounds:
         _raise_oob(oob, "genome-wide")
     keys = keys[:2 * pairs.n]
-    # padding keys are ~0: they sort last on every digit, so sorting the low 2*col_bits bits
+    # padding keys are ~0: they sort last on every digit, so sorting the low key_sort_bits(nbins) bits
     # (rounded up to whole 8-bit digits) leaves the real keys first and in order
-    skeys, free = sort_keys_u64(keys, 2 * col_bits) if pairs.n else (keys, None)
+    skeys, free = sort_keys_u64(keys, key_sort_bits(nbins)) if pairs.n else (keys, None)
     row_ptr, col, cnt = keys_to_csr(skeys, n_valid, col_bits, nbins, scratch=free)
     return SymCsr(row_ptr, col, cnt, nbins)
 

@@ -281,6 +281,110 @@ def impute_inter_chromosomal(un: dict, imp: dict, mm: PairColumns, pp: PairColum
 # ======================================================================================
 # (c) two-step allelic correction
 # ======================================================================================
+def _f64_device(X):
+    """float64 device copy (row-major) of a host matrix or device tensor."""
+    if isinstance(X, torch.Tensor):
+        return X.to(device=require_cuda(), dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(X), dtype=np.float64)).to(require_cuda())
+
+
+def _row_nnz(Matrix):
+    """Per-row non-zero counts on the device: (int32 device tensor, nrows, ncols)."""
+    dev = require_cuda()
+    if isinstance(Matrix, torch.Tensor) or np.issubdtype(np.asarray(Matrix).dtype, np.floating):
+        t = _f64_device(Matrix)
+        nr, nc = t.shape
+        nz = torch.empty(nr, dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().hc_rownnz_f64(kernels.ptr(t), t.stride(0), nr, nc, kernels.ptr(nz), kernels.stream_ptr()),
+                   "hc_rownnz_f64")
+        return nz, nr, nc
+    M = np.asarray(Matrix)
+    if M.shape[0] != M.shape[1]:
+        return _row_nnz(M.astype(np.float64))
+    b = DenseBatch.from_numpy([M])
+    _, nz = kernels.rowstats(b.buf.data_ptr(), b.lds[0], b.sizes[0], b.sizes[0], dev)
+    return nz, b.sizes[0], b.sizes[0]
+
+
+def _gap_rows(Matrix, gap_mode):
+    nz, nr, nc = _row_nnz(Matrix)
+    dev = nz.device
+    cov = torch.empty(nr, dtype=torch.float64, device=dev)
+    gf = torch.empty(nr, dtype=torch.uint8, device=dev)
+    gi = torch.empty(nr, dtype=torch.int32, device=dev)
+    ng = torch.zeros(1, dtype=torch.int32, device=dev)
+    _abi.check(_abi.lib().hc_gap_rows(kernels.ptr(nz), nr, nc, gap_mode, kernels.ptr(cov), kernels.ptr(gf), kernels.ptr(gi),
+                                      kernels.ptr(ng), kernels.stream_ptr()), "hc_gap_rows")
+    return cov, gf, gi, int(ng.item())
+
+
+def Coverage_M(Matrix):
+    """matrixBuilding.py:904-912 -- fraction of non-zero entries per row."""
+    return _gap_rows(Matrix, _abi.HC_GAP_FIXED)[0].cpu().numpy()
+
+
+def Gap_defined(Matrix):
+    """matrixBuilding.py:915-929 -- rows whose coverage is below min(25th percentile of the non-zero
+    coverages, 0.2).  A matrix without a covered row has no percentile: the reference raises IndexError
+    there (np.percentile of an empty array), and so does this."""
+    cov, _, gi, n = _gap_rows(Matrix, _abi.HC_GAP_PERCENTILE)
+    if not bool((cov != 0).any().item()):
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")     # what np.percentile([]) raises
+    return _gap_array(gi, n)
+
+
+def Gap_definedLowRes(Matrix):
+    """matrixBuilding.py:742-753 -- fixed 0.1 coverage threshold."""
+    _, _, gi, n = _gap_rows(Matrix, _abi.HC_GAP_FIXED)
+    return _gap_array(gi, n)
+
+
+def Non_Gap_Defined(N, gap):
+    """matrixBuilding.py:932-943 -- the rows of range(N) that are not gaps (host: O(N) index bookkeeping)."""
+    keep = np.ones(int(N), dtype=bool)
+    g = np.asarray(gap, dtype=np.int64)
+    keep[g[(g >= 0) & (g < N)]] = False
+    return np.nonzero(keep)[0] if keep.any() else np.array([])
+
+
+Non_Gap_DefinedLowRes = Non_Gap_Defined          # matrixBuilding.py:756-767: same body
+
+
+def Trans2symmetry(Matrix, gap):
+    """matrixBuilding.py:945-979 -- no gap rows: S_ij + S_ji off the diagonal; otherwise max for pairs of
+    gap rows and the mean for every other pair; the diagonal is kept."""
+    S = _f64_device(Matrix)
+    n = S.shape[0]
+    assert S.shape[1] == n
+    gap = np.asarray(gap)
+    gf = None
+    if gap.size:
+        flags = np.zeros(n, dtype=np.uint8)
+        flags[gap.astype(np.int64)] = 1
+        gf = torch.from_numpy(flags).to(S.device)
+    out = torch.empty_like(S)
+    _abi.check(_abi.lib().hc_trans2symmetry_f64(kernels.ptr(S), S.stride(0), n, kernels.ptr(gf), kernels.ptr(out),
+                                                out.stride(0), kernels.stream_ptr()), "hc_trans2symmetry_f64")
+    return out.cpu().numpy()
+
+
+def Trans2symmetryLowRes(Matrix):
+    """matrixBuilding.py:770-776."""
+    return Trans2symmetry(Matrix, np.array([]))
+
+
+def Correct_VC(X, alpha):
+    """matrixBuilding.py:780-790 -- one-shot vanilla-coverage style scaling
+    x / (colsum**alpha [None, :] * rowsum**alpha [:, None]), zero sums replaced by 1."""
+    x = _f64_device(X)
+    nr, nc = x.shape
+    out = torch.empty_like(x)
+    work = torch.empty(int(_abi.lib().hc_correct_vc_work_bytes(nr, nc)), dtype=torch.uint8, device=x.device)
+    _abi.check(_abi.lib().hc_correct_vc_f64(kernels.ptr(x), x.stride(0), nr, nc, float(alpha), kernels.ptr(out), out.stride(0),
+                                            kernels.ptr(work), kernels.stream_ptr()), "hc_correct_vc_f64")
+    return out.cpu().numpy()
+
+
 def _gap_array(idx_t, count):
     # the reference returns np.array(python list): int64, or float64 when empty
     return idx_t[:count].cpu().numpy().astype(np.int64) if count else np.array([])

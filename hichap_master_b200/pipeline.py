@@ -51,6 +51,10 @@ class LocalStage:
         self.bin_work = None
         self.side = torch.cuda.Stream(device=self.dev)
         self.copy = torch.cuda.Stream(device=self.dev)
+        # out-of-range pairs (position beyond the chromosome end): counted on the device during binning,
+        # read once per run where the results are synchronised anyway (the reference raises IndexError)
+        self.oob = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.oob_host = torch.zeros(1, dtype=torch.int64).pin_memory()
 
     def upload(self, hp: HostPairs) -> PairColumns:
         assert hp.n <= self.max_pairs
@@ -67,10 +71,12 @@ class LocalStage:
         runs] -> filters -> ICE."""
         b = self.batch
         b.buf.zero_()
+        self.oob.zero_()
         if self.banded:
-            self.bin_work = kernels.bin_pairs_local_banded(pairs, res, b, check_bounds=False, work=self.bin_work)
+            self.bin_work = kernels.bin_pairs_local_banded(pairs, res, b, check_bounds=False, work=self.bin_work,
+                                                           oob=self.oob)
         else:
-            kernels.bin_pairs_local(pairs, res, b, check_bounds=False)
+            kernels.bin_pairs_local(pairs, res, b, check_bounds=False, oob=self.oob)
         return self._after_binning(records, weights_to_host, **ice_kw)
 
     def run_from_host(self, hp: HostPairs, res: int, records=False, weights_to_host=True, chunk_pairs=1 << 24,
@@ -82,7 +88,8 @@ class LocalStage:
         b, n = self.batch, hp.n
         main = torch.cuda.current_stream()
         b.buf.zero_()
-        bb = kernels.BandedBinning(b, res, work=self.bin_work)
+        self.oob.zero_()
+        bb = kernels.BandedBinning(b, res, work=self.bin_work, oob=self.oob)
         ready = torch.cuda.Event()
         ready.record(main)                 # the device columns may still be read by work queued earlier on `main`
         self.copy.wait_event(ready)
@@ -112,12 +119,17 @@ class LocalStage:
             with torch.cuda.stream(self.side):
                 recs, nbytes = kernels.dense_batch_triu_records(b, self.pool, sync=False)
             d2h += nbytes
+        self.oob_host.copy_(self.oob, non_blocking=True)       # 8 bytes; complete before ice_dense_iterate returns
         params = kernels.ice_params(**ice_kw)
         bias = kernels.ice_dense_filters(b, params)
         results, info = kernels.ice_dense_iterate(b, bias, params)
+        n_oob = int(self.oob_host.item())
+        if n_oob:
+            raise IndexError("%d pair(s) fall outside the intra-chromosomal matrices (position beyond the "
+                             "chromosome length in the genomeSize file)" % n_oob)
         if weights_to_host:
             self.weights_host.copy_(bias, non_blocking=False)
             d2h += 8 * b.nbins
         if records:
             self.side.synchronize()
-        return dict(bias=bias, results=results, info=info, records=recs, d2h_bytes=d2h)
+        return dict(bias=bias, results=results, info=info, records=recs, d2h_bytes=d2h, oob_pairs=n_oob)

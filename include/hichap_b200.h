@@ -34,7 +34,7 @@ extern "C" {
 #define HC_ERR_NCCL (-3)
 #define HC_ERR_UNSUPPORTED (-4)
 
-#define HC_ABI_VERSION 1
+#define HC_ABI_VERSION 2
 
 int hc_version(void);
 /* Optional, once per device: keep the library's stream-ordered scratch cached between calls. */
@@ -205,7 +205,8 @@ typedef struct hc_ice_run_info {
 /* Iterate every problem of the dense batch to convergence, independently (own loop, scale and
  * early exit -- cooler's _balance_cisonly; one problem == _balance_genomewide).
  * bias: in = initial bias from the filters, out = final weights (NaN for masked bins, divided
- * by sqrt(scale) when rescale_marginals).  work: 3*nbins doubles.  The reduction over the
+ * by sqrt(scale) when rescale_marginals).  All scratch is stream-ordered and library-owned (ABI v1 took a
+ * `work` pointer here that was never used; v2 drops it).  The reduction over the
  * marginals, the bias update, the rescale and the convergence test all run on the device
  * (stream kernel + per-chromosome update kernel, replayed as a CUDA graph); the host only polls a
  * done counter.  By default the tiles are first re-encoded into uint8 + an overflow list (exact; a
@@ -214,7 +215,7 @@ typedef struct hc_ice_run_info {
 int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n,
                          const int32_t* mat_ld, const int64_t* bin_off, int32_t nprob,
                          const int32_t* h_mat_n, const hc_ice_params* h_params, double* bias,
-                         double* work, hc_ice_result* results, hc_ice_run_info* h_info, void* stream);
+                         hc_ice_result* results, hc_ice_run_info* h_info, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (a') Sort path: pairs -> keys -> radix sort -> reduce-by-key -> SYMMETRIC CSR (both triangles
@@ -336,6 +337,28 @@ int hc_twostep_batch(const int32_t* tmats, const int64_t* t_off, const int32_t* 
                      const int64_t* h_hoff, const int32_t* h_hld, const int64_t* h_tbin, const int64_t* h_hbin,
                      double* out, const int64_t* h_out_off, double* alpha, uint8_t* gapflag, int32_t* gapidx,
                      int32_t* ngap, void* work, void* stream);
+
+/* The reference's own building blocks, separately callable (SURVEY.md section 8b keeps Correct_VC(X, alpha)
+ * among the signatures; hc_twostep_correct fuses all of them for the int32 tiles).  Float64 matrices,
+ * row-major with leading dimension ld.
+ *   hc_rownnz_f64          non-zero entries per row: Coverage_M = 1 - zeros/len (matrixBuilding.py:904-912);
+ *                          integer matrices use hc_rowstats_i32.
+ *   hc_gap_rows            coverage[n], gap flags and the ascending gap-row list from the per-row non-zero
+ *                          counts: Gap_defined (:915-929, HC_GAP_PERCENTILE) / Gap_definedLowRes (:742-753,
+ *                          HC_GAP_FIXED).  Non_Gap_Defined (:932-943) is the complement (gapflag == 0).
+ *   hc_trans2symmetry_f64  Trans2symmetry (:945-979): gapflag == NULL -> S_ij + S_ji (also
+ *                          Trans2symmetryLowRes :770-776); else both rows gaps -> max, otherwise mean; the
+ *                          diagonal is copied.  out must not alias S.
+ *   hc_correct_vc_f64      Correct_VC (:780-790): x / (colsum^alpha [None,:] * rowsum^alpha [:,None]), zero
+ *                          sums -> 1.  work: hc_correct_vc_work_bytes(nrows, ncols). */
+int hc_rownnz_f64(const double* M, int64_t ld, int32_t nrows, int32_t ncols, int32_t* rownnz, void* stream);
+int hc_gap_rows(const int32_t* rownnz, int32_t n, int32_t ncols, int32_t gap_mode, double* coverage,
+                uint8_t* gapflag, int32_t* gapidx, int32_t* ngap, void* stream);
+int hc_trans2symmetry_f64(const double* S, int64_t ld, int32_t n, const uint8_t* gapflag, double* out,
+                          int64_t ld_out, void* stream);
+int64_t hc_correct_vc_work_bytes(int32_t nrows, int32_t ncols);
+int hc_correct_vc_f64(const double* X, int64_t ld, int32_t nrows, int32_t ncols, double alpha, double* out,
+                      int64_t ld_out, void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Valid-pair text ingest (host, multithreaded): parses the 23-column

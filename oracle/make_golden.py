@@ -11,6 +11,7 @@ Fixtures (all < 1 MB):
                          raw traditional / un-imputed / imputed matrices, two-step corrected
                          matrices and gap lists, GenomeWideMatrixCorrection output
   twostep_cases.npz      TwoStepCorrection (:984-1023) on a gap-free and a gappy triple
+  building_blocks.npz    Coverage_M, Gap_defined(+LowRes), Non_Gap_Defined, Trans2symmetry(+LowRes), Correct_VC
   ice_restated.npz       NOT from the reference (its ICE is the un-vendored `cooler`): outputs of
                          oracle/cooler_ice.py, kept as a regression anchor ("parity unpinned")
 """
@@ -228,6 +229,34 @@ def make_twostep_cases():
     return out
 
 
+def make_building_blocks():
+    """The reference's own helper functions on the inputs of twostep_cases.npz (plus a rectangular
+    Correct_VC case): Coverage_M :904, Gap_defined :915, Gap_definedLowRes :742, Non_Gap_Defined :932,
+    Trans2symmetry :945, Trans2symmetryLowRes :770, Correct_VC :780."""
+    mod = ref_shim.load()
+    g = np.load(os.path.join(GOLDEN, "twostep_cases.npz"), allow_pickle=True)
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag in ("nogap", "gappy"):
+        mm = g[tag + "|MM"]
+        gap = np.asarray(mod.Gap_defined(mm))
+        S = mm / rng.uniform(0.3, 1.0, size=mm.shape[0])[:, None]          # what TwoStepCorrection feeds (:1007)
+        sym = mod.Trans2symmetry(S, gap)
+        out.update({tag + "|M": mm, tag + "|Coverage": mod.Coverage_M(mm), tag + "|Gap": gap,
+                    tag + "|GapLowRes": np.asarray(mod.Gap_definedLowRes(mm)),
+                    tag + "|NonGap": np.asarray(mod.Non_Gap_Defined(mm.shape[0], gap)),
+                    tag + "|S": S, tag + "|Sym": sym, tag + "|SymLowRes": mod.Trans2symmetryLowRes(S),
+                    tag + "|VC": mod.Correct_VC(sym, 2.0 / 3)})
+    # the max rule needs two gap rows with asymmetric entries between them
+    S = rng.gamma(1.0, 2.0, size=(40, 40)); S[rng.random((40, 40)) < 0.5] = 0.0
+    gap = np.array([3, 4, 17, 39])
+    out.update({"forced|S": S, "forced|Gap": gap, "forced|Sym": mod.Trans2symmetry(S, gap)})
+    X = rng.poisson(2.0, size=(37, 53)).astype(float); X[5, :] = 0; X[:, 11] = 0
+    out.update({"rect|X": X, "rect|VC": mod.Correct_VC(X, 0.5)})
+    np.savez_compressed(os.path.join(GOLDEN, "building_blocks.npz"), **out)
+    return out
+
+
 def make_ice_restated(trad):
     """Regression anchor for the cooler restatement (NOT a reference output)."""
     out = {}
@@ -272,6 +301,7 @@ def main():
     make_allelic()
     make_imputation()
     make_twostep_cases()
+    make_building_blocks()
     make_ice_restated(trad)
     for f in sorted(os.listdir(GOLDEN)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(GOLDEN, f))))

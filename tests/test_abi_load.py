@@ -31,7 +31,7 @@ def test_bindings_cover_the_header():
 def test_version_and_error_string_without_gpu():
     from hichap_master_b200 import _abi
     lib = _abi.lib()
-    assert lib.hc_version() == 1
+    assert lib.hc_version() == 2
     assert isinstance(lib.hc_last_error(), bytes)
     assert lib.hc_launch_count() >= 0
 

@@ -344,6 +344,28 @@ def test_two_step_golden_cases(mb):
         check_matrix(npm, g[tag + "|Nor_PM"], tag + " Nor_PM")
 
 
+def test_standalone_building_blocks_golden(mb):
+    """Correct_VC, Coverage_M, Gap_defined(+LowRes), Non_Gap_Defined, Trans2symmetry(+LowRes) with the
+    reference's signatures, against outputs of the reference functions themselves."""
+    g = load_golden("building_blocks.npz")
+    for tag in ("nogap", "gappy"):
+        M = g[tag + "|M"]
+        for mat in (M, M.astype(np.float64)):                       # integer tiles and the float64 kernel
+            assert np.array_equal(mb.Coverage_M(mat), g[tag + "|Coverage"]), tag
+            assert gaps_equal(mb.Gap_defined(mat), g[tag + "|Gap"]), tag
+            assert gaps_equal(mb.Gap_definedLowRes(mat), g[tag + "|GapLowRes"]), tag
+        assert gaps_equal(mb.Non_Gap_Defined(M.shape[0], g[tag + "|Gap"]), g[tag + "|NonGap"])
+        assert gaps_equal(mb.Non_Gap_DefinedLowRes(M.shape[0], g[tag + "|Gap"]), g[tag + "|NonGap"])
+        sym = mb.Trans2symmetry(g[tag + "|S"], g[tag + "|Gap"])
+        check_matrix(sym, g[tag + "|Sym"], tag + " Trans2symmetry")
+        check_matrix(mb.Trans2symmetryLowRes(g[tag + "|S"]), g[tag + "|SymLowRes"], tag + " Trans2symmetryLowRes")
+        check_matrix(mb.Correct_VC(g[tag + "|Sym"], 2.0 / 3), g[tag + "|VC"], tag + " Correct_VC")
+    check_matrix(mb.Trans2symmetry(g["forced|S"], g["forced|Gap"]), g["forced|Sym"], "forced gap pairs (max rule)")
+    check_matrix(mb.Correct_VC(g["rect|X"], 0.5), g["rect|VC"], "rectangular Correct_VC")
+    with pytest.raises(IndexError):
+        mb.Gap_defined(np.zeros((5, 5), dtype=np.int64))            # no covered row: np.percentile([]) in the reference
+
+
 def test_intra_chrom_correction_golden(mb):
     g = load_golden("allelic_small.npz")
     res = "80000"

@@ -208,3 +208,19 @@ def test_inter_chromosomal_imputation_matches_reference_golden(small_genome_file
             assert np.array_equal(imp[res], g["case%d|imp|%d" % (k, res)]), (k, res)
             fired += int((imp[res] - cis_only[res]).sum())
     assert fired > 1000          # the fixtures do exercise the neighbourhood vote
+
+
+def test_building_blocks_golden():
+    """oracle restatements of the reference's helper functions vs outputs of the reference itself
+    (Coverage_M :904, Gap_defined :915, Gap_definedLowRes :742, Trans2symmetry :945, Correct_VC :780)."""
+    g = load_golden("building_blocks.npz")
+    for tag in ("nogap", "gappy"):
+        M = g[tag + "|M"]
+        assert np.array_equal(ho.coverage(M), g[tag + "|Coverage"])
+        assert np.array_equal(np.asarray(ho.gap_defined(M), np.int64), np.asarray(g[tag + "|Gap"], np.int64))
+        assert np.array_equal(np.asarray(ho.gap_defined_lowres(M), np.int64), np.asarray(g[tag + "|GapLowRes"], np.int64))
+        np.testing.assert_allclose(ho.trans2symmetry(g[tag + "|S"], g[tag + "|Gap"]), g[tag + "|Sym"], rtol=1e-14)
+        np.testing.assert_allclose(ho.trans2symmetry(g[tag + "|S"], np.array([])), g[tag + "|SymLowRes"], rtol=1e-14)
+        np.testing.assert_allclose(ho.correct_vc(g[tag + "|Sym"], 2.0 / 3), g[tag + "|VC"], rtol=1e-13)
+    np.testing.assert_allclose(ho.trans2symmetry(g["forced|S"], g["forced|Gap"]), g["forced|Sym"], rtol=1e-14)
+    np.testing.assert_allclose(ho.correct_vc(g["rect|X"], 0.5), g["rect|VC"], rtol=1e-13)
