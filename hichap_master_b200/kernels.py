@@ -478,6 +478,11 @@ def nccl_comm_init(uid: bytes, nranks: int, rank: int) -> int:
     return int(comm.value)
 
 
+def nccl_allreduce_f64(comm: int, t):
+    """In-place sum-allreduce of a float64 device tensor on the library's communicator (current stream)."""
+    check(lib().hc_nccl_allreduce_sum_f64(C.c_void_p(comm), ptr(t), int(t.numel()), stream_ptr()), "hc_nccl_allreduce_sum_f64")
+
+
 def nccl_comm_destroy(comm: int):
     check(lib().hc_nccl_comm_destroy(C.c_void_p(comm)), "hc_nccl_comm_destroy")
 

@@ -136,3 +136,24 @@ def test_ice_csr_end_to_end_vs_oracle(K, cuda_device, kw):
     ref, rst = cooler_ice.balance(key // total, key % total, cnt, total, off, cis_only=False, **kw)
     check_weights(w, ref, "e2e %r" % (kw,))
     assert st["iters"] == rst["iters"] and st["converged"] == rst["converged"]
+
+
+def test_power_of_two_bins_last_diagonal_cell_survives_padding(K, cuda_device):
+    """nbins == 2^col_bits (256 bins): the key of cell (255, 255) is all ones in the low 2*col_bits bits and would tie
+    with the padding key of dropped pairs; the sort must look at one more bit (kernels.key_sort_bits)."""
+    import torch
+    from hichap_master_b200 import kernels
+    from hichap_master_b200.device import PairColumns
+    res, nb = 1000, 256
+    assert kernels.key_sort_bits(nb) == 17 and kernels.key_sort_bits(255) == 16 and kernels.key_sort_bits(257) == 18
+    # dropped pairs (filtered chromosome -1) come FIRST in the input: a stable sort on 16 bits would leave their
+    # padding keys in front of the (255, 255) key
+    c1 = np.array([-1, -1, -1, 0, 0, 0, 0], np.int32)
+    p1 = np.array([5, 5, 5, 255_500, 255_100, 1_000, 254_000], np.int32)
+    p2 = np.array([5, 5, 5, 255_900, 255_200, 2_000, 255_999], np.int32)
+    start = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    chrom_bins = torch.tensor([nb], dtype=torch.int32, device=cuda_device)
+    csr = kernels.pairs_to_csr(PairColumns(c1, p1, c1, p2, device=cuda_device), res, start, chrom_bins, nb, False)
+    b1, b2, v = (t.cpu().numpy() for t in kernels.csr_upper_records(csr))
+    got = {(int(a), int(b)): int(c) for a, b, c in zip(b1, b2, v)}
+    assert got == {(1, 2): 1, (254, 255): 1, (255, 255): 2}

@@ -303,6 +303,33 @@ def test_ice_encodings_and_kernel_variants(mb, monkeypatch, env, sizes, kw):
     _ice_vs_oracle(mb, mats, "variant %r %r" % (env, kw), **kw)
 
 
+def test_ice_packed_wide_bias_range_matches_int32_path(mb, monkeypatch):
+    """Biases spread over more than 2^20 within one chromosome: the fixed-point byte planes of the packed kernel
+    lose low mantissa bits of the small biases (rounded to nearest).  NaN mask and iteration count must equal
+    the int32 / fp64 path and the oracle; weights stay within the tolerance."""
+    n, rng = 640, np.random.default_rng(5)
+    expo = np.linspace(0.0, 21.0, n)                        # row scales 2^-21 .. 1  ->  weights spread over > 2^20
+    s = 2.0 ** (-expo)
+    rng.shuffle(s)
+    d = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) + 1.0
+    lam = 4.0e7 * s[:, None] * s[None, :] / d
+    M = rng.poisson(np.minimum(lam, 2.0e9 / n)).astype(np.int64)
+    M = np.triu(M) + np.triu(M, 1).T
+    kw = dict(mad_max=0, min_nnz=1, max_iters=300)
+    w_packed, st_packed = mb.ice_balance_dense([M], **kw)
+    monkeypatch.setenv("HC_ICE_PACKED", "0")
+    w_i32, st_i32 = mb.ice_balance_dense([M], **kw)
+    x, y = np.nonzero(np.triu(M))
+    ref, rst = cooler_ice.balance(x, y, M[x, y], n, [0, n], cis_only=True, **kw)
+    ok = ~np.isnan(ref)
+    print("bias range 2^%.1f; iters packed %r int32 %r oracle %r" % (np.log2(np.nanmax(ref) / np.nanmin(ref)), st_packed["iters"], st_i32["iters"], rst["iters"]))
+    assert np.nanmax(ref) / np.nanmin(ref) > 2.0 ** 20
+    assert np.array_equal(np.isnan(w_packed), np.isnan(w_i32)) and np.array_equal(np.isnan(w_packed), np.isnan(ref))
+    assert st_packed["iters"] == st_i32["iters"] == rst["iters"]
+    check_weights(w_packed, ref, "packed, wide bias range")
+    check_weights(w_i32, ref, "int32, wide bias range")
+
+
 def test_ice_more_than_8192_columns(mb):
     """A matrix wider than the cluster update kernel covers (8 x 256 x 4 columns): generic update path on the
     packed encoding, several K-segments."""
