@@ -16,6 +16,11 @@
 #include "hc_common.cuh"
 
 int hc_nccl_allreduce_f64(void* comm, const double* send, double* recv, size_t count, cudaStream_t s);  // hc_nccl.cu
+// hc_ice_csrb.cu: the column-blocked encoding (default); returns +1 when a count does not fit its 19 bits
+int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const int32_t* cnt, int64_t row0, int64_t nloc,
+                               const int64_t* bin_off, int32_t nprob, const int64_t* h_bin_off, const hc_ice_params* P,
+                               double* bias, hc_ice_result* results, hc_ice_run_info* h_info, void* nccl_comm,
+                               cudaStream_t caller);
 
 namespace {
 
@@ -345,6 +350,17 @@ extern "C" int hc_ice_csr_balance(const int64_t* row_ptr, const int32_t* col, co
     const long long nbins = h_bin_off[nprob];
     if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 0; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; h_info->stream_full_ms = 0.f; h_info->stream_full_launches = 0; }
     if (nbins == 0) return HC_OK;
+    {
+        // default: column-blocked 4-byte entries with the bias block staged in shared memory (hc_ice_csrb.cu);
+        // HC_CSR_BLOCKED=0 (A/B) or a count beyond 19 bits -> the row-major gather kernel below
+        bool blocked = true;
+        if (const char* e = getenv("HC_CSR_BLOCKED")) blocked = atoi(e) != 0;
+        if (blocked) {
+            const int r = hc_ice_csr_balance_blocked(row_ptr, col, cnt, row0, nloc, bin_off, nprob, h_bin_off, P, bias, results,
+                                                     h_info, nccl_comm, s);
+            if (r <= 0) return r;
+        }
+    }
 
     double* marg = reinterpret_cast<double*>(work);
     // sharded: the stream kernel writes the local rows of marg_local (zero elsewhere, zeroed once)

@@ -453,7 +453,16 @@ def ice_balance_csr(csr: SymCsr, prob_off, chrom_off=None, comm=None, allreduce=
     results = res.cpu().numpy().view(rdt)
     stats = dict(tol=params.tol, min_nnz=params.min_nnz, min_count=params.min_count, mad_max=params.mad_max,
                  cis_only=nprob > 1, ignore_diags=params.ignore_diags, divisive_weights=False,
-                 launches=int(info.launches), loop_ms=float(info.loop_ms))
+                 launches=int(info.launches), loop_ms=float(info.loop_ms), pack_ms=float(info.pack_ms),
+                 stream_full_ms=float(info.stream_full_ms), stream_full_launches=int(info.stream_full_launches))
+    if int(info.packed) == 2:       # column-blocked encoding (hc_ice_csrb.cu): 4-byte entries, padded segments
+        stats.update(encoding="column-blocked symmetric CSR: 4 B per stored entry (13-bit column in an 8192-bin block + 19-bit "
+                              "weighted count), bias block staged in shared memory by cp.async.bulk",
+                     stored_entries=int(info.overflow_cells),
+                     bytes_per_entry=4.0 * int(info.overflow_cells) / max(csr.nnz, 1))
+    else:
+        stats.update(encoding="row-major symmetric CSR: int32 column + int32 count per stored entry, bias gathered from L2",
+                     stored_entries=int(csr.nnz), bytes_per_entry=8.0)
     if nprob == 1:
         stats.update(scale=float(results["scale"][0]), var=float(results["var"][0]),
                      converged=bool(results["converged"][0]), iters=int(results["iters"][0]))

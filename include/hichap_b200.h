@@ -195,9 +195,10 @@ typedef struct hc_ice_result {
 typedef struct hc_ice_run_info {
     int32_t launches; /* kernels launched by the call (iterations + finalise)                  */
     float loop_ms;    /* device time of the iteration loop (CUDA events on `stream`)           */
-    int32_t packed;   /* dense: 1 when the loop streamed the uint8 + overflow encoding         */
+    int32_t packed;   /* dense: 1 when the loop streamed the uint8 + overflow encoding; CSR: 2 = column-blocked */
     float pack_ms;    /* dense: device time of building that encoding (once per call)          */
-    int64_t overflow_cells; /* dense, packed: cells whose weighted count exceeds 255           */
+    int64_t overflow_cells; /* dense, packed: cells whose weighted count exceeds 255; CSR, packed == 2 (column-blocked
+                               4-byte entries): stored entries incl. segment padding                              */
     float stream_full_ms;   /* dense, HC_ICE_TIME_KERNEL=1: mean duration of a stream-kernel launch  */
     int32_t stream_full_launches; /* ... over this many launches in which every problem was active */
 } hc_ice_run_info;
@@ -270,7 +271,11 @@ int hc_ice_csr_marginals(const int64_t* row_ptr, const int32_t* col, const int32
                          int64_t nloc, int32_t ignore_diags, double* nnz_marg, double* marg,
                          void* stream);
 
-/* Balance to convergence (one problem per [bin_off[p], bin_off[p+1]) range: one range =
+/* Balance to convergence.  By default the CSR is first re-encoded (once per call, stream-ordered scratch of ~4 B per
+ * stored entry) into column blocks of 8192 bins with 4-byte entries so that the bias of a block is staged in shared
+ * memory (cp.async.bulk) instead of being gathered from L2, and the whole iteration -- stream kernel, marginal
+ * reduction, the NCCL allreduce, cluster update kernel -- is replayed as a CUDA graph (HC_CSR_BLOCKED=0 or a count
+ * beyond 19 bits: row-major gather kernel).  One problem per [bin_off[p], bin_off[p+1]) range: one range =
  * genome-wide; per-chromosome ranges on cis-only keys = `--cis-only`).  bias: in = initial
  * bias from hc_ice_filter_bins, out = final weights.  nccl_comm: NULL on one GPU, otherwise a
  * communicator from hc_nccl_comm_init -- the marginal vector is then allreduced in-stream once

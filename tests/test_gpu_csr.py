@@ -99,10 +99,12 @@ def check_weights(w, ref, what):
     assert err < RTOL, what
 
 
-@pytest.mark.parametrize("window", ["0", "1"])
-def test_ice_csr_restated_golden(K, cuda_device, monkeypatch, window):
-    """window=1: the opt-in stream kernel that stages a bias window with a TMA bulk copy (HC_CSR_WINDOW)."""
+@pytest.mark.parametrize("window,blocked", [("0", "1"), ("0", "0"), ("1", "0")])
+def test_ice_csr_restated_golden(K, cuda_device, monkeypatch, window, blocked):
+    """blocked=1: the default column-blocked encoding (hc_ice_csrb.cu); blocked=0: the row-major gather kernel;
+    window=1: its opt-in variant that stages a bias window with a TMA bulk copy (HC_CSR_WINDOW)."""
     monkeypatch.setenv("HC_CSR_WINDOW", window)
+    monkeypatch.setenv("HC_CSR_BLOCKED", blocked)
     g = load_golden("ice_restated.npz")
     off = g["chrom_offsets"]
     n = int(off[-1])
@@ -157,3 +159,64 @@ def test_power_of_two_bins_last_diagonal_cell_survives_padding(K, cuda_device):
     b1, b2, v = (t.cpu().numpy() for t in kernels.csr_upper_records(csr))
     got = {(int(a), int(b)): int(c) for a, b, c in zip(b1, b2, v)}
     assert got == {(1, 2): 1, (254, 255): 1, (255, 255): 2}
+
+
+def _banded_pixels(n, seed, band, far_per_row, big=None):
+    """upper-triangular pixels of an n-bin matrix: a dense band (long segments in the diagonal column block), random
+    far pixels (short segments in every other block), a masked stretch of rows, optionally one huge count"""
+    rng = np.random.default_rng(seed)
+    bias = np.exp(rng.normal(0, 0.3, n))
+    b1, b2, cnt = [], [], []
+    for k in range(0, band):
+        i = np.arange(n - k)
+        v = rng.poisson(60.0 / (k + 1) * bias[i] * bias[i + k])
+        keep = v > 0
+        b1.append(i[keep]); b2.append(i[keep] + k); cnt.append(v[keep])
+    m = n * far_per_row
+    i = rng.integers(0, n, m); j = rng.integers(0, n, m)
+    lo, hi = np.minimum(i, j), np.maximum(i, j)
+    ok = hi - lo >= band
+    key = np.unique(lo[ok].astype(np.int64) * n + hi[ok])
+    b1.append(key // n); b2.append(key % n); cnt.append(rng.integers(1, 4, key.size))
+    b1, b2, cnt = (np.concatenate(x) for x in (b1, b2, cnt))
+    dead = (b1 >= 3000) & (b1 < 3040) | (b2 >= 3000) & (b2 < 3040)
+    b1, b2, cnt = b1[~dead], b2[~dead], cnt[~dead].astype(np.int64)
+    if big is not None:
+        cnt[np.argmax((b1 == 100) & (b2 == 101))] = big
+    o = np.lexsort((b2, b1))
+    return b1[o], b2[o], cnt[o]
+
+
+@pytest.mark.parametrize("n,band,far,cis,kw", [
+    (20_000, 12, 6, False, dict()),                 # 3 column blocks: long diagonal-block segments, short far ones
+    (20_000, 300, 2, False, dict(ignore_diags=0, max_iters=40)),  # segments of several hundred entries (whole-warp groups); diagonal counted twice
+    (9_000, 4, 2, False, dict(ignore_diags=2, min_nnz=1, mad_max=0, max_iters=50)),     # very short segments (2-lane groups)
+    (26_000, 12, 4, True, dict(max_iters=60)),      # cis-only: 4 problems, chromosome borders inside column blocks
+])
+def test_ice_csr_column_blocked_vs_oracle(K, cuda_device, n, band, far, cis, kw):
+    b1, b2, cnt = _banded_pixels(n, 3 + band, band, far)
+    off = np.array([0, n // 3, n // 2, n - 700, n], np.int64) if cis else np.array([0, n // 2, n], np.int64)
+    if cis:         # cis-only keys: drop the pixels between different chromosomes
+        ch = np.searchsorted(off[1:], np.arange(n), side="right")
+        keep = ch[b1] == ch[b2]
+        b1, b2, cnt = b1[keep], b2[keep], cnt[keep]
+    csr = csr_from_pixels(K, cuda_device, b1, b2, cnt, n)
+    bias, st = K.ice_balance_csr(csr, off if cis else np.array([0, n]), chrom_off=off, **kw)
+    assert "column-blocked" in st["encoding"]
+    ref, rst = cooler_ice.balance(b1, b2, cnt, n, off, cis_only=cis, **kw)
+    check_weights(bias.cpu().numpy(), ref, "blocked n=%d band=%d" % (n, band))
+    assert st["iters"] == rst["iters"]
+    if cis:
+        assert st["converged_per_chrom"] == rst["converged_per_chrom"]
+        np.testing.assert_allclose(st["scale"], rst["scale"], rtol=RTOL)
+
+
+def test_ice_csr_count_beyond_19_bits_uses_the_row_major_kernel(K, cuda_device):
+    n = 9_000
+    b1, b2, cnt = _banded_pixels(n, 8, 6, 2, big=700_000)
+    csr = csr_from_pixels(K, cuda_device, b1, b2, cnt, n)
+    bias, st = K.ice_balance_csr(csr, np.array([0, n]))
+    assert "row-major" in st["encoding"]
+    ref, rst = cooler_ice.balance(b1, b2, cnt, n, np.array([0, n]), cis_only=False)
+    check_weights(bias.cpu().numpy(), ref, "count overflow fallback")
+    assert st["iters"] == rst["iters"]
