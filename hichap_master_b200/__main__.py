@@ -44,10 +44,16 @@ def run(argv=None):
     logging.addLevelName(21, "main")                       # scripts/hichap:463-479
     logging.basicConfig(filename=os.path.join(args.workspace, args.logFile), level=21,
                         format="%(name)-25s %(levelname)-7s @ %(asctime)s: %(message)s")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                       # launched with torchrun: one rank per GPU
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     from .matrixBuilding import HaplotypeMatrixConstruction, TraditionalMatrixConstruction
     whole = args.wholeRes or []
-    if not os.path.exists(args.out):
-        os.mkdir(args.out)
+    os.makedirs(args.out, exist_ok=True)
     if args.NonAllelic:
         TraditionalMatrixConstruction(OutPath=args.out, RepPath=args.bedPath, genomeSize=args.genomeSize,
                                       wholeRes=whole, localRes=args.localRes, chroms=args.chroms)
@@ -56,6 +62,10 @@ def run(argv=None):
                                     wholeRes=whole, localRes=args.localRes, Imputation_ratio=args.ImputationRatio,
                                     Imputation_min=args.ImputationMin, Imputation_region=args.ImputationRegion,
                                     chroms=args.chroms)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -28,9 +28,9 @@ import torch
 
 from . import _abi, kernels
 from .device import DenseBatch, PairColumns, require_cuda
-from .matrixBuilding import (GenomeWideMatrixCorrection, IntraMatrixToSparseDict, Load_Genome, Sort_Chromosomes,
+from .matrixBuilding import (CisCsr, GenomeWideMatrixCorrection, IntraMatrixToSparseDict, Load_Genome, Sort_Chromosomes,
                              WholeMatrixToSparseDict, _bins_from_genome, _start_table, bin_traditional,
-                             chrom_offsets_from_bins, impute_inter_chromosomal)
+                             chrom_offsets_from_bins, ice_balance_sparse, impute_inter_chromosomal)
 from .pairs import read_pair_files
 
 log = logging.getLogger(__name__)
@@ -69,14 +69,46 @@ class MatrixStore:
             self.data["bins|%d" % res] = np.array([(k, v[0], v[1]) for k, v in bins.items()],
                                                   dtype=[("chrom", "U16"), ("start", "<i8"), ("end", "<i8")])
 
-    def set_weight(self, res, weight, stats):
+    def set_weight(self, res, weight, stats, names=None):
+        """``names``: chromosomes (in order) the weight vector covers when this rank balanced only its own
+        chromosomes; the pieces of all ranks are gathered and rank 0 stores the full vector."""
+        dist, rank, world = _dist()
+        if names is not None and world > 1:
+            pieces = [None] * world
+            dist.all_gather_object(pieces, (list(names), np.asarray(weight), stats))
+            if rank != 0:
+                return
+            self.data["weight_chroms|%d" % res] = np.array([c for nm, _, _ in pieces for c in nm])
+            weight = np.concatenate([w for _, w, _ in pieces])
+            stats = dict(stats, iters=[i for _, _, st in pieces for i in st["iters"]],
+                         scale=np.concatenate([np.atleast_1d(st["scale"]) for _, _, st in pieces]))
+        elif world > 1 and rank != 0:
+            return
         self.data["weight|%d" % res] = weight
         self.data["weight_attrs|%d" % res] = np.array(repr({k: (v.tolist() if isinstance(v, np.ndarray) else v)
                                                             for k, v in stats.items()}))
 
     def save(self):
-        np.savez(self.path, **self.data)
-        return self.path
+        _, rank, world = _dist()
+        path = self.path if rank == 0 else self.path[:-4] + ".part%d.npz" % rank
+        if rank == 0 and world > 1:
+            self.data["parts"] = np.array(world)
+        np.savez(path, **self.data)
+        return path
+
+    @staticmethod
+    def load(path):
+        """{key: array} of a store, the per-rank parts concatenated in rank order (row blocks / chromosomes are
+        assigned to ranks in ascending order of rows, so record order is preserved)."""
+        main = dict(np.load(path, allow_pickle=True))
+        for r in range(1, int(main.get("parts", 1))):
+            part = np.load(path[:-4] + ".part%d.npz" % r, allow_pickle=True)
+            for k in part.files:
+                if k in main and main[k].dtype.names and part[k].dtype.names:
+                    main[k] = np.concatenate([main[k], part[k]])
+                elif k not in main:
+                    main[k] = part[k]
+        return main
 
 
 def _add_into(dst: DenseBatch, src: DenseBatch):
@@ -94,12 +126,22 @@ def _balance(store, whole, local, wholeRes, localRes):
     (matrixBuilding.py:706-714)."""
     for res in wholeRes:
         bins, W = whole[res]
-        off = torch.from_numpy(chrom_offsets_from_bins(bins)).to(W.device)
-        w, st = kernels.ice_balance_dense(W, off, ignore_diags=1)
+        if isinstance(W, kernels.SymCsr):              # sort path (dense tiles would not fit) / row-block shard
+            w, st = ice_balance_sparse(W, bins, cis_only=False, ignore_diags=1, comm=getattr(W, "comm", None),
+                                       allreduce=getattr(W, "allreduce", None))
+        else:
+            off = torch.from_numpy(chrom_offsets_from_bins(bins)).to(W.device)
+            w, st = kernels.ice_balance_dense(W, off, ignore_diags=1)
         store.set_weight(res, w, st)
     for res in localRes:
-        w, st = kernels.ice_balance_dense(local[res], None, ignore_diags=1)
-        store.set_weight(res, w, st)
+        L = local[res]
+        if isinstance(L, CisCsr):
+            w, st = ice_balance_sparse(L.csr, L.bins, cis_only=True, ignore_diags=1)
+            names = L.order
+        else:
+            w, st = kernels.ice_balance_dense(L, None, ignore_diags=1)
+            names = getattr(L, "chrom_names", None)
+        store.set_weight(res, w, st, names=names if _dist()[2] > 1 else None)
 
 
 def _store_traditional(path, genome, whole, local):
@@ -108,41 +150,118 @@ def _store_traditional(path, genome, whole, local):
     for res, (bins, W) in whole.items():
         store.add(res, WholeMatrixToSparseDict(bins, W), bins)
     for res, L in local.items():
+        if isinstance(L, CisCsr):
+            store.add(res, L.records())
+            continue
         recs, _ = kernels.dense_batch_triu_records(L)
-        store.add(res, {c: recs[i].copy() for i, c in enumerate(order)})
+        store.add(res, {c: recs[i].copy() for i, c in enumerate(getattr(L, "chrom_names", order))})
     return store
+
+
+def _dist():
+    """(torch.distributed, rank, world) when the process runs under torchrun with an initialised group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+_COMM = {}
+
+
+def _library_comm(dev):
+    """one NCCL communicator of the library per process (in-loop allreduce of the row-block sharded ICE)"""
+    from . import distributed as hd
+    if "comm" not in _COMM:
+        _COMM["comm"] = hd.nccl_comm_from_process_group(dev)
+    return _COMM["comm"]
+
+
+def _bin_replicate(cols, genome, wholeRes, localRes, dev):
+    """Binning of one replicate's host columns.  One process: ``bin_traditional`` (dense tiles, or the sort path when
+    they would not fit).  Under torchrun: genome-wide matrices become row-block sharded CSRs
+    (each rank sorts a slice of the pairs, keys are exchanged), intra-chromosomal matrices are LPT-sharded by
+    chromosome -- every rank bins and balances only its own chromosomes, no collective on that path."""
+    dist, rank, world = _dist()
+    c1, p1, c2, p2 = cols
+    if world == 1:
+        return bin_traditional(PairColumns(c1, p1, c2, p2, device=dev), genome, wholeRes, localRes, dev)
+    from . import distributed as hd, shard
+    from .matrixBuilding import _check_fits, _dense_bytes, bin_traditional_sparse, dense_budget_bytes
+    order = Sort_Chromosomes(genome)
+    whole, local = {}, {}
+    if wholeRes:
+        sl = slice(rank, None, world)
+        pr = PairColumns(c1[sl], p1[sl], c2[sl], p2[sl], device=dev)
+        comm = _library_comm(dev)
+        for res in wholeRes:
+            bins, total = _bins_from_genome(genome, res, [(c, c) for c in order])
+            start = _start_table(bins, order, dev)
+            chrom_bins = torch.tensor([genome[c] // res + 1 for c in order], dtype=torch.int32, device=dev)
+            csr, _ = hd.build_row_block_csr(pr, res, start, chrom_bins, total)
+            csr.comm, csr.allreduce = comm, (lambda t: dist.all_reduce(t))
+            whole[res] = (bins, csr)
+    for res in localRes:
+        sizes = [genome[c] // res + 1 for c in order]
+        mine = shard.chromosome_shards(sizes, world)[rank]
+        remap = np.full(len(order) + 1, -1, np.int32)
+        remap[mine] = np.arange(len(mine), dtype=np.int32)
+        lc = np.where(c1 == c2, remap[np.where(c1 >= 0, c1, len(order))], -1).astype(np.int32)
+        sel = lc >= 0
+        pr = PairColumns(lc[sel], p1[sel], lc[sel], p2[sel], device=dev)
+        names = [order[i] for i in mine]
+        my_sizes = [sizes[i] for i in mine]
+        if _dense_bytes(my_sizes) > dense_budget_bytes(dev):
+            bins, csr = bin_traditional_sparse(pr, {c: genome[c] for c in names}, res, cis_only=True, device=dev)
+            local[res] = CisCsr(csr, bins, names)
+        else:
+            _check_fits(_dense_bytes(my_sizes), dev, "intra-chromosomal %d bp" % res)
+            L = DenseBatch(my_sizes, dev)
+            L.chrom_names = names
+            kernels.bin_pairs_local_banded(pr, res, L)
+            local[res] = L
+    return whole, local
+
+
+def _is_sparse(whole, local):
+    return any(isinstance(W, kernels.SymCsr) for _, W in whole.values()) or any(isinstance(L, CisCsr) for L in local.values())
 
 
 def TraditionalMatrixConstruction(OutPath, RepPath, genomeSize, wholeRes, localRes, chroms=["#", "X"],
                                   balance=True):
     """matrixBuilding.py:617-717.  Writes ``Cooler/{prefix}Multi.npz`` per replicate and
-    ``Cooler/Merged_Multi.npz``; returns the list of written files."""
+    ``Cooler/Merged_Multi.npz``; returns the list of written files.  Under torchrun every rank writes the
+    records it owns (``*.partK.npz`` for rank K > 0; ``MatrixStore.load`` reassembles them) and rank 0 the weights."""
     _say("Building Replicate Matrix respectively")
     dev = require_cuda()
     CoolerPath = os.path.join(OutPath, "Cooler")
     os.makedirs(CoolerPath, exist_ok=True)
     genome = Load_Genome(genomeSize, chroms)
     order = Sort_Chromosomes(genome)
-    written, merged = [], None
+    written, merged, all_cols = [], None, []
     for rep_p in RepPath:
         files = [i for i in os.listdir(rep_p) if "_Valid.bed" in i]
         prefix = files[0].split("Valid")[0]
         files = [os.path.join(rep_p, f) for f in files]
         c1, p1, c2, p2, _ = read_pair_files(files, order, chroms, "valid23")   # `cat files` + per-line parse
-        whole, local = bin_traditional(PairColumns(c1, p1, c2, p2, device=dev), genome, wholeRes, localRes, dev)
+        whole, local = _bin_replicate((c1, p1, c2, p2), genome, wholeRes, localRes, dev)
         store = _store_traditional(os.path.join(CoolerPath, prefix + "Multi.npz"), genome, whole, local)
         if balance:
             _balance(store, whole, local, wholeRes, localRes)
         written.append(store.save())
         _say("    %s finished" % store.path)
+        all_cols.append((c1, p1, c2, p2))
         if merged is None:
             merged = (whole, local)
-        else:                                    # cooler.merge_coolers (:692) sums the pixels
+        elif not _is_sparse(whole, local):          # cooler.merge_coolers (:692) sums the pixels
             for res in wholeRes:
                 _add_into(merged[0][res][1], whole[res][1])
             for res in localRes:
                 _add_into(merged[1][res], local[res])
     _say("Merging the replicates ...")
+    if len(RepPath) > 1 and _is_sparse(*merged):    # sparse matrices: the merged pixels are those of the concatenated pairs
+        del whole, local
+        merged = _bin_replicate(tuple(np.concatenate([c[k] for c in all_cols]) for k in range(4)), genome, wholeRes, localRes, dev)
     store = _store_traditional(os.path.join(CoolerPath, "Merged_Multi.npz"), genome, merged[0], merged[1])
     if balance:
         _say("    Balancing start ...")
@@ -196,7 +315,7 @@ def _haplotype_counts(bed_files, genome, wholeRes, localRes, chroms, dev, imputa
         cols[tag] = PairColumns(c1, p1, c2, p2, mark, dev)
     # traditional matrices: all five classes together (:1081-1094)
     allp = PairColumns(*(torch.cat([getattr(cols[t], a) for t in cols]) for a in ("c1", "p1", "c2", "p2")), device=dev)
-    data.tra_whole, data.tra_local = bin_traditional(allp, genome, wholeRes, localRes, dev)
+    data.tra_whole, data.tra_local = bin_traditional(allp, genome, wholeRes, localRes, dev, budget=1 << 62)   # the correction reads dense tiles
     sizes = lambda res: [genome[c] // res + 1 for c in order]
     for res in localRes:
         # haplotype local matrices live in one batch: M chromosomes then P chromosomes

@@ -99,20 +99,79 @@ def _to_pair_columns(bed_IO, order, chroms, layout, device):
     return PairColumns(c1, p1, c2, p2, mark, device)
 
 
-def bin_traditional(pairs: PairColumns, genome: dict, wholeRes, localRes, device=None):
-    """Device-resident binning: returns ({res: (bins, DenseBatch[1])}, {res: DenseBatch[nchrom]})
-    with chromosomes in ``Sort_Chromosomes`` order.  matrixBuilding.py:553-603."""
+def dense_budget_bytes(device=None) -> int:
+    """Largest dense int32 tile set the binning may allocate before it switches to the sort path (symmetric
+    CSR).  The reference always allocates ``np.zeros((Sum, Sum))`` (matrixBuilding.py:559), which at 10 kb
+    genome-wide is 369 GB.  ``HC_DENSE_BUDGET_GB`` overrides; default: a third of the device memory."""
+    import os
+    env = os.environ.get("HC_DENSE_BUDGET_GB")
+    if env is not None:
+        return int(float(env) * 1e9)
+    dev = require_cuda(device)
+    return int(torch.cuda.get_device_properties(dev).total_memory // 3)
+
+
+def _dense_bytes(sizes) -> int:
+    return int(sum(4 * n * max(128, (n + 127) // 128 * 128) for n in sizes))
+
+
+def _check_fits(nbytes, dev, what):
+    free, _ = torch.cuda.mem_get_info(dev)
+    if nbytes > free:
+        raise MemoryError("the dense %s matrices need %.1f GB of device memory (%.1f GB free); this entry point returns "
+                          "dense matrices like the reference -- use the sparse path (bin_traditional_sparse / "
+                          "TraditionalMatrixBuilding) for this resolution" % (what, nbytes / 1e9, free / 1e9))
+
+
+class CisCsr:
+    """All intra-chromosomal matrices of one resolution as ONE symmetric CSR over the concatenated bins (keys built
+    cis-only): the sparse counterpart of the per-chromosome ``DenseBatch``."""
+
+    def __init__(self, csr, bins, order):
+        self.csr, self.bins, self.order = csr, bins, list(order)
+        self.off = chrom_offsets_from_bins(bins)
+
+    def records(self):
+        """{chrom: upper-triangular S_dtype records in chromosome-local coordinates} (matrixBuilding.py:508-524)"""
+        b1, b2, v = (t.cpu().numpy() for t in kernels.csr_upper_records(self.csr))
+        cut = np.searchsorted(b1, self.off)
+        out = {}
+        for i, c in enumerate(self.order):
+            lo, hi = int(cut[i]), int(cut[i + 1])
+            rec = np.zeros(hi - lo, dtype=S_dtype)
+            rec["bin1"], rec["bin2"], rec["IF"] = b1[lo:hi].astype(np.int64) - self.off[i], b2[lo:hi].astype(np.int64) - self.off[i], v[lo:hi]
+            out[c] = rec
+        return out
+
+
+def bin_traditional(pairs: PairColumns, genome: dict, wholeRes, localRes, device=None, budget=None):
+    """Device-resident binning: returns ({res: (bins, DenseBatch[1] | SymCsr)}, {res: DenseBatch[nchrom] | CisCsr})
+    with chromosomes in ``Sort_Chromosomes`` order.  matrixBuilding.py:553-603.  Matrices whose dense int32 tiles
+    exceed ``budget`` bytes (``dense_budget_bytes``) go through the sort path (radix sort + reduce-by-key into a
+    symmetric CSR) instead of the dense accumulation."""
     dev = require_cuda(device)
     order = Sort_Chromosomes(genome)
+    budget = dense_budget_bytes(dev) if budget is None else int(budget)
     whole, local = {}, {}
     for res in wholeRes:
         bins, total = _bins_from_genome(genome, res, [(c, c) for c in order])
-        W = DenseBatch([total], dev)
         start = _start_table(bins, order, dev)
+        if _dense_bytes([total]) > budget:
+            chrom_bins = torch.tensor([genome[c] // res + 1 for c in order], dtype=torch.int32, device=dev)
+            whole[res] = (bins, kernels.pairs_to_csr(pairs, res, start, chrom_bins, total, False))
+            continue
+        _check_fits(_dense_bytes([total]), dev, "genome-wide %d bp" % res)
+        W = DenseBatch([total], dev)
         kernels.bin_pairs_whole(pairs, res, start, start, W)
         whole[res] = (bins, W)
     for res in localRes:
-        L = DenseBatch([genome[c] // res + 1 for c in order], dev)   # matrixBuilding.py:564
+        sizes = [genome[c] // res + 1 for c in order]                # matrixBuilding.py:564
+        if _dense_bytes(sizes) > budget:
+            bins, csr = bin_traditional_sparse(pairs, genome, res, cis_only=True, device=dev)
+            local[res] = CisCsr(csr, bins, order)
+            continue
+        _check_fits(_dense_bytes(sizes), dev, "intra-chromosomal %d bp" % res)
+        L = DenseBatch(sizes, dev)
         kernels.bin_pairs_local_banded(pairs, res, L)            # freshly zeroed tiles: symmetric on entry
         local[res] = L
     return whole, local
@@ -122,6 +181,8 @@ def WholeMatrixToSparseDict(Bins, Matrix):
     """matrixBuilding.py:457-506.  ``Matrix`` may be a NumPy array (uploaded) or a 1-matrix
     ``DenseBatch`` already in HBM.  Intra blocks: upper triangle; inter blocks ``c1_c2`` (c1
     before c2 in sorted order): all non-zeros, block-local coordinates."""
+    if isinstance(Matrix, kernels.SymCsr):
+        return WholeCsrToSparseDict(Bins, Matrix)
     W = Matrix if isinstance(Matrix, DenseBatch) else DenseBatch.from_numpy([np.asarray(Matrix)])
     ld, base = W.lds[0], W.buf.data_ptr()
     chroms = Sort_Chromosomes(Bins.keys())
@@ -173,6 +234,9 @@ def TraditionalMatrixBuilding(bed_IO, genomeSize, wholeRes, localRes, chroms):
     Whole_Lib = {res: WholeMatrixToSparseDict(bins, W) for res, (bins, W) in whole.items()}
     Local_Lib = {}
     for res, L in local.items():
+        if isinstance(L, CisCsr):
+            Local_Lib[res] = L.records()
+            continue
         recs, _ = kernels.dense_batch_triu_records(L)
         Local_Lib[res] = {c: recs[i].copy() for i, c in enumerate(order)}   # own the memory (pool is reused)
     return Whole_Lib, Local_Lib
@@ -185,7 +249,7 @@ def TraditionalMatrixInAllelic(bed_IO, genomeSize, wholeRes, localRes, chroms):
     order = Sort_Chromosomes(genome)
     dev = require_cuda()
     pairs = _to_pair_columns(bed_IO, order, chroms, "allelic", dev)
-    whole, local = bin_traditional(pairs, genome, wholeRes, localRes, dev)
+    whole, local = bin_traditional(pairs, genome, wholeRes, localRes, dev, budget=1 << 62)   # dense by contract
     Whole_Lib = {res: {"Bins": bins, "Matrix": W.to_numpy(0)} for res, (bins, W) in whole.items()}
     Local_Lib = {res: {c: L.to_numpy(i) for i, c in enumerate(order)} for res, L in local.items()}
     return Whole_Lib, Local_Lib

@@ -141,3 +141,66 @@ def test_traditional_construction_two_replicates(cuda_device, tmp_path, small_ge
     assert np.array_equal(np.isnan(w), np.isnan(ref))
     ok = ~np.isnan(ref)
     assert np.max(np.abs(w[ok] - ref[ok]) / ref[ok]) < RTOL
+
+
+def _write_replicates(tmp_path, n_pairs=150_000, seeds=(51, 52)):
+    genome = {c: l for c, l in SMALL_GENOME.items() if c != "M"}
+    names = list(genome)
+    reps = []
+    for i, seed in enumerate(seeds):
+        d = tmp_path / ("rep%d" % i); d.mkdir()
+        c1, p1, c2, p2 = synth.genome_pairs(genome, names, n_pairs, seed, trans_frac=0.2)
+        with open(d / ("R%d_Valid.bed" % i), "w") as fh:
+            fh.writelines(synth.valid23_lines(names, c1, p1, c2, p2))
+        reps.append(str(d))
+    return reps
+
+
+def _stores_equal(a, b, what):
+    keys = sorted(k for k in a if "|" in k and not k.startswith(("weight", "bins")))
+    assert keys == sorted(k for k in b if "|" in k and not k.startswith(("weight", "bins"))), what
+    for k in keys:
+        assert all(np.array_equal(a[k][f], b[k][f]) for f in ("bin1", "bin2", "IF")), (what, k)
+    for k in (k for k in a if k.startswith("weight|")):
+        wa, wb = a[k], b[k]
+        assert np.array_equal(np.isnan(wa), np.isnan(wb)), (what, k)
+        ok = ~np.isnan(wa)
+        assert np.max(np.abs(wa[ok] - wb[ok]) / np.abs(wa[ok])) < RTOL, (what, k)
+
+
+def test_traditional_construction_sort_path_equals_dense_path(cuda_device, tmp_path, small_genome_file, monkeypatch):
+    """The drop-in picks the sort path (symmetric CSR, CSR ICE) by itself when the dense tiles exceed the budget
+    (genome-wide 10 kb would be 369 GB): with the budget forced to zero the stores must equal the dense-path
+    stores -- records bit-exact, weights within tolerance -- replicate merge included."""
+    from hichap_master_b200 import matrixBuilding as mb
+    from hichap_master_b200.construction import MatrixStore
+    reps = _write_replicates(tmp_path)
+    dense = str(tmp_path / "dense"); os.makedirs(dense)
+    mb.TraditionalMatrixConstruction(dense, reps, small_genome_file, [500000], [40000], CHROMS)
+    monkeypatch.setenv("HC_DENSE_BUDGET_GB", "0")
+    sparse = str(tmp_path / "sparse"); os.makedirs(sparse)
+    mb.TraditionalMatrixConstruction(sparse, reps, small_genome_file, [500000], [40000], CHROMS)
+    for f in ("R0_Multi.npz", "R1_Multi.npz", "Merged_Multi.npz"):
+        a, b = MatrixStore.load(os.path.join(dense, "Cooler", f)), MatrixStore.load(os.path.join(sparse, "Cooler", f))
+        _stores_equal(a, b, f)
+    # and the callable itself
+    text = open(os.path.join(reps[0], "R0_Valid.bed")).read()
+    import io
+    w1, l1 = mb.TraditionalMatrixBuilding(io.StringIO(text), small_genome_file, [500000], [40000], CHROMS)
+    monkeypatch.delenv("HC_DENSE_BUDGET_GB")
+    w0, l0 = mb.TraditionalMatrixBuilding(io.StringIO(text), small_genome_file, [500000], [40000], CHROMS)
+    for lib0, lib1 in ((w0[500000], w1[500000]), (l0[40000], l1[40000])):
+        assert set(lib0) == set(lib1)
+        for k in lib0:
+            assert all(np.array_equal(lib0[k][f], lib1[k][f]) for f in ("bin1", "bin2", "IF")), k
+
+
+def test_dense_entry_points_refuse_impossible_allocations(cuda_device, small_genome_file, tmp_path):
+    """TraditionalMatrixInAllelic returns dense matrices by contract: a resolution whose tiles cannot fit raises
+    MemoryError instead of dying inside the allocator."""
+    from hichap_master_b200 import matrixBuilding as mb
+    import io
+    big = tmp_path / "genomeSize_big"
+    big.write_text("chr1\t249250621\nchr2\t243199373\n")
+    with pytest.raises(MemoryError):
+        mb.TraditionalMatrixInAllelic(io.StringIO("chr1\t100\tchr1\t5000\n"), str(big), [500], [], CHROMS)
