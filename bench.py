@@ -279,13 +279,24 @@ def run_ours(args):
     # roofline of the dominant kernel (the fused ICE iteration), from the same timed steps
     iters = out["results"]["iters"].astype(np.int64)
     info = out["info"]
-    packed = bool(info.packed)
+    mode = int(info.packed)            # 3: symmetric blocks, persistent dataflow kernel; 1: full-matrix uint8; 0: int32 tiles
+    packed = mode != 0
     # algorithmic bytes of the stream kernel: the matrix once per iteration -- SURVEY 8(d) counts 4 B per cell (int32
-    # tiles); the packed encoding (default) streams 1 B per cell + 8 B per overflow cell (col, extra count)
+    # tiles); the packed encoding streams 1 B per cell + 8 B per overflow cell (col, extra count); the symmetric
+    # encoding (default) streams only the 256 x 256 uint8 blocks on or above the diagonal
     cell_iters = float(sum(int(it) * n * n for it, n in zip(iters, sizes)))
     mean_iters = cell_iters / max(float(sum(n * n for n in sizes)), 1.0)
-    ice_bytes = (1.0 * cell_iters + 8.0 * float(info.overflow_cells) * mean_iters) if packed else 4.0 * cell_iters
-    ice_kernel = "ice_q8_mma_kernel" if packed else "ice_dense_stream_kernel"
+    nblk = [(n + 255) // 256 for n in sizes]
+    sym_bytes = [65536.0 * nb * (nb + 1) // 2 for nb in nblk]
+    if mode == 3:
+        ice_bytes = float(sum(int(it) * b for it, b in zip(iters, sym_bytes))) + 8.0 * float(info.overflow_cells) * mean_iters
+        ice_kernel = "sym_ice_kernel"
+    elif mode == 1:
+        ice_bytes = 1.0 * cell_iters + 8.0 * float(info.overflow_cells) * mean_iters
+        ice_kernel = "ice_q8_mma_kernel"
+    else:
+        ice_bytes = 4.0 * cell_iters
+        ice_kernel = "ice_dense_stream_kernel"
     loop_ms = float(info.loop_ms)
     n_iter_launches = int(max(iters)) if len(iters) else 0
 
@@ -379,11 +390,14 @@ def run_ours(args):
     # the stream kernel on its own: the first launch of every graph replay is bracketed by CUDA events inside the graph
     # (HC_ICE_TIME_KERNEL=1) and those with all chromosomes still active are averaged; falls back to the loop-level figure
     sq = float(sum(n * n for n in sizes))
-    full_bytes = (1.0 if packed else 4.0) * sq + (8.0 * float(info.overflow_cells) if packed else 0.0)
+    if mode == 3:       # ONE launch runs every iteration of every chromosome: the launch's bytes are the loop's bytes
+        full_bytes, survey_bytes = ice_bytes, 4.0 * cell_iters
+    else:
+        full_bytes = (1.0 if packed else 4.0) * sq + (8.0 * float(info.overflow_cells) if packed else 0.0)
+        survey_bytes = 4.0 * sq      # dense-tile ICE iteration = 4*N^2
     kernel_ms = float(info.stream_full_ms) if int(info.stream_full_launches) > 0 else 0.0
     achieved = full_bytes / (kernel_ms * 1e6) if kernel_ms > 0 else loop_achieved
     launch_ms = kernel_ms if kernel_ms > 0 else loop_ms / max(n_iter_launches, 1)
-    survey_bytes = 4.0 * sq      # dense-tile ICE iteration = 4*N^2
     cfg = workload_config(args.pairs)
     cfg.update({"parallelism": "chromosomes LPT-sharded by N^2 over %d GPU(s), no collective" % world,
                 "host_format": "pinned columns: chromosome uint8 + mid-point int32 per mate (10 B/pair)",
@@ -393,6 +407,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None,
         "dtype": "int32 counts (ICE streams them as u8 + overflow list, s32 tensor-core plane sums) / f64 weights" if packed else "int32 counts / f64 weights",
+        "ice_mode": {3: "symmetric blocks, persistent dataflow kernel", 1: "full-matrix uint8, one launch pair per iteration", 0: "int32 tiles"}.get(mode),
         "data": "synthetic", "config": cfg,
         "throughput_Mpairs_per_s": args.pairs / (ms_step * 1e3),
         "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
@@ -403,7 +418,10 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                      "algorithmic_bytes_per_launch": full_bytes if kernel_ms > 0 else ice_bytes / max(n_iter_launches, 1),
-                     "bytes_definition": ("packed encoding: 1 B per cell + 8 B per overflow cell -- the bytes this kernel must stream"
+                     "bytes_definition": ("symmetric packed encoding: the 256 x 256 uint8 blocks on or above the diagonal, once per iteration of "
+                                          "each chromosome, + 8 B per overflow cell -- the bytes this kernel must stream; one launch = the whole loop"
+                                          if mode == 3 else
+                                          "packed encoding: 1 B per cell + 8 B per overflow cell -- the bytes this kernel must stream"
                                           if packed else "int32 tiles: 4 B per cell (SURVEY 8d)"),
                      "survey_4N2": {"algorithmic_bytes_per_launch": survey_bytes, "effective": survey_bytes / (launch_ms * 1e6) if launch_ms > 0 else 0.0,
                                     "frac": survey_bytes / (launch_ms * 1e6) / peak if launch_ms > 0 else 0.0,
@@ -411,12 +429,16 @@ def run_ours(args):
                                             "packed encoding moves a quarter of those bytes, exactly"},
                      "launches": int(info.stream_full_launches) if kernel_ms > 0 else n_iter_launches,
                      "avg_launch_ms": launch_ms,
-                     "timing": ("CUDA events around the first stream-kernel launch of every graph replay of the last timed step in "
+                     "timing": ("CUDA events around the single persistent launch that runs all iterations of all chromosomes "
+                                "(block streaming, partial-sum reduction, bias update and convergence test inside it)") if mode == 3 else
+                               ("CUDA events around the first stream-kernel launch of every graph replay of the last timed step in "
                                 "which every chromosome was still active (event-record nodes inside the replayed graph)") if kernel_ms > 0
                                else "CUDA events around the whole iteration loop (stream + update kernels, launch gaps, polls)",
                      "loop": {"achieved": loop_achieved, "frac": loop_achieved / peak, "ms": loop_ms, "launches": n_iter_launches,
                               "note": "algorithmic bytes of all iterations / time of the whole loop incl. update kernels and gaps"},
-                     "encoding": ("uint8 cells + overflow list, built once per call in %.3f ms (%d overflow cells)"
+                     "encoding": ("upper-triangular 256 x 256 uint8 blocks + overflow list, built once per call in %.3f ms (%d overflow cells)"
+                                  % (float(info.pack_ms), int(info.overflow_cells))) if mode == 3 else
+                                 ("uint8 cells + overflow list, built once per call in %.3f ms (%d overflow cells)"
                                   % (float(info.pack_ms), int(info.overflow_cells))) if packed else "int32 tiles",
                      "traffic": traffic, "traffic_note": traffic_note},
         "roofline_secondary": secondary,

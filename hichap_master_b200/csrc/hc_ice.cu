@@ -34,6 +34,11 @@
 #include "hc_common.cuh"
 #include "hc_select.cuh"
 
+// hc_ice_sym.cu
+int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const int32_t* mat_n, const int32_t* mat_ld,
+                             const int64_t* bin_off, int32_t nprob, const int32_t* h_mat_n, const hc_ice_params* P,
+                             double* bias, hc_ice_result* results, hc_ice_run_info* h_info, cudaStream_t s);
+
 namespace {
 
 __device__ __forceinline__ double band_weight(int j, int r, int kd) {
@@ -974,8 +979,15 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     // variant: 4 rows per warp step is the fastest per byte, but a warp item is at least RG rows; when the
     // batch is small (one large chromosome per GPU in the 8-way sharded run) fewer rows per item keep
     // every resident warp busy.  HC_ICE_VARIANT overrides (tuning).
-    bool packed = true;    // uint8 + overflow encoding of the tiles (see the file header); HC_ICE_PACKED=0: stream the int32 tiles
-    if (const char* e = getenv("HC_ICE_PACKED")) packed = atoi(e) != 0;
+    // HC_ICE_PACKED: 2 (default) = symmetric packed blocks + persistent dataflow kernel (hc_ice_sym.cu); 1 = full-matrix
+    // uint8 + overflow encoding streamed once per iteration by the kernels below; 0 = stream the int32 tiles
+    int mode = 1;   // TODO(validate on hardware, then default 2)
+    if (const char* e = getenv("HC_ICE_PACKED")) mode = atoi(e);
+    if (mode >= 2) {
+        const int r = hc_ice_dense_balance_sym(mats, mat_off, mat_n, mat_ld, bin_off, nprob, h_mat_n, P, bias, results, h_info, s);
+        if (r <= 0) return r;       // +1: not applicable (a chromosome beyond 8192 bins): full-matrix packed kernel
+    }
+    bool packed = mode != 0;
     int64_t total_rows = 0;
     for (int p = 0; p < nprob; ++p) total_rows += h_mat_n[p];
     StreamVariant V;

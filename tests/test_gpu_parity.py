@@ -292,6 +292,13 @@ def _ice_vs_oracle(mb, mats, what, **kw):
     ({"HC_ICE_KSEG": "8", "HC_ICE_Q8_VARIANT": "0"}, (900, 40), dict()),   # two strips per work item
     ({"HC_ICE_CLUSTER_UPDATE": "0"}, (700, 333), dict()),            # single-CTA update kernel on the packed encoding
     ({"HC_ICE_PACKED": "0"}, (700, 333), dict()),                    # int32 tiles, fp64 FMA kernel
+    ({"HC_ICE_PACKED": "1"}, (700, 333), dict()),                    # full-matrix packed encoding, one launch pair per iteration
+    ({"HC_ICE_PACKED": "2"}, (700, 333), dict()),                    # symmetric blocks, persistent dataflow kernel (3 + 2 blocks per side)
+    ({"HC_ICE_PACKED": "2"}, (700, 333), dict(ignore_diags=0)),      # ... kept diagonal: half weights on the stored diagonal
+    ({"HC_ICE_PACKED": "2"}, (700, 333), dict(ignore_diags=3)),
+    ({"HC_ICE_PACKED": "2"}, (256, 257, 40, 1), dict()),             # block edges, a single-block and a 1-bin chromosome
+    ({"HC_ICE_PACKED": "2"}, (2100,), dict(max_iters=7)),            # 9 blocks per side, stops at max_iters
+    ({"HC_ICE_PACKED": "2"}, (1500, 900, 333, 90, 64), dict(mad_max=0, min_nnz=0)),   # five chromosomes in flight at once
 ])
 def test_ice_encodings_and_kernel_variants(mb, monkeypatch, env, sizes, kw):
     """Every stream / update kernel variant of hc_ice_dense_balance against the oracle, with counts far above 255
@@ -316,6 +323,9 @@ def test_ice_packed_wide_bias_range_matches_int32_path(mb, monkeypatch):
     M = rng.poisson(np.minimum(lam, 2.0e9 / n)).astype(np.int64)
     M = np.triu(M) + np.triu(M, 1).T
     kw = dict(mad_max=0, min_nnz=1, max_iters=300)
+    monkeypatch.setenv("HC_ICE_PACKED", "2")
+    w_sym, st_sym = mb.ice_balance_dense([M], **kw)
+    monkeypatch.setenv("HC_ICE_PACKED", "1")
     w_packed, st_packed = mb.ice_balance_dense([M], **kw)
     monkeypatch.setenv("HC_ICE_PACKED", "0")
     w_i32, st_i32 = mb.ice_balance_dense([M], **kw)
@@ -326,6 +336,8 @@ def test_ice_packed_wide_bias_range_matches_int32_path(mb, monkeypatch):
     assert np.nanmax(ref) / np.nanmin(ref) > 2.0 ** 20
     assert np.array_equal(np.isnan(w_packed), np.isnan(w_i32)) and np.array_equal(np.isnan(w_packed), np.isnan(ref))
     assert st_packed["iters"] == st_i32["iters"] == rst["iters"]
+    assert st_sym["iters"] == rst["iters"] and np.array_equal(np.isnan(w_sym), np.isnan(ref))
+    check_weights(w_sym, ref, "symmetric packed, wide bias range")
     check_weights(w_packed, ref, "packed, wide bias range")
     check_weights(w_i32, ref, "int32, wide bias range")
 
