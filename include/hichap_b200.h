@@ -366,6 +366,26 @@ int hc_correct_vc_f64(const double* X, int64_t ld, int32_t nrows, int32_t ncols,
                       int64_t ld_out, void* work, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * First downstream consumers of the stage's outputs (HiCHap/StructureFind.py).
+ * Float64 matrices are row-major n x n with leading dimension ld.
+ *   hc_balance_apply_i32         out = nan_to_num(count * w_i * w_j): what cooler.matrix(balance=True).fetch() +
+ *                                np.nan_to_num hand to CallPeaks (StructureFind.py:2005-2007)
+ *   hc_colnnz_f64                non-zero entries per COLUMN: Distance_Decay's own gap rule (:216-221)
+ *   hc_distance_sums_f64         dsum[d] = sum of M[i][j], |i-j| = d, column j not flagged (both triangles): the
+ *                                bincount of Distance_Decay (:225-253); the O(n) gap normalisation stays on the host
+ *   hc_observed_expected_f64     M[i][j] / decline[|i-j|] where M != 0 (Get_PCA :321-326)
+ *   hc_directionality_index_f64  Get_DI (:804-840): chitest = 0 t-test flavour, 1 chi-square flavour
+ * ---------------------------------------------------------------------------------------- */
+int hc_balance_apply_i32(const int32_t* M, int64_t ld, int32_t n, const double* weight, double* out, int64_t ld_out,
+                         void* stream);
+int hc_colnnz_f64(const double* M, int64_t ld, int32_t n, int32_t* colnnz, void* stream);
+int hc_distance_sums_f64(const double* M, int64_t ld, int32_t n, const uint8_t* gapflag, double* dsum, void* stream);
+int hc_observed_expected_f64(const double* M, int64_t ld, int32_t n, const double* decline, double* out, int64_t ld_out,
+                             void* stream);
+int hc_directionality_index_f64(const double* M, int64_t ld, int32_t n, const uint8_t* gapflag, const int32_t* window_bin,
+                                int32_t chitest, double* di, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Valid-pair text ingest (host, multithreaded): parses the 23-column
  * *_Valid.bed (layout 0: chromosomes in columns 1 and 8, fragment mid-points in columns 6 and 13;
  * matrixBuilding.py:573-586) or the 4/5-column allelic beds (layout 1: c1 p1 c2 p2 [mark];

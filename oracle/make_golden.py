@@ -11,6 +11,7 @@ Fixtures (all < 1 MB):
                          raw traditional / un-imputed / imputed matrices, two-step corrected
                          matrices and gap lists, GenomeWideMatrixCorrection output
   twostep_cases.npz      TwoStepCorrection (:984-1023) on a gap-free and a gappy triple
+  consumers.npz          StructureFind.py: Distance_Decay, the O/E loop of Get_PCA, Get_DI, bias_handle
   building_blocks.npz    Coverage_M, Gap_defined(+LowRes), Non_Gap_Defined, Trans2symmetry(+LowRes), Correct_VC
   ice_restated.npz       NOT from the reference (its ICE is the un-vendored `cooler`): outputs of
                          oracle/cooler_ice.py, kept as a regression anchor ("parity unpinned")
@@ -257,6 +258,61 @@ def make_building_blocks():
     return out
 
 
+class _GapArray(np.ndarray):
+    """ndarray whose ``== None`` is a plain False, as it was for the NumPy the 2019 reference ran on (the reference tests
+    ``if G_array == None`` at StructureFind.py:215; NumPy 2 would compare elementwise and the ``if`` would raise)."""
+
+    def __eq__(self, other):
+        if other is None:
+            return False
+        return np.ndarray.__eq__(self, other)
+
+    __hash__ = None
+
+
+def make_consumers():
+    """Outputs of the reference's StructureFind methods that first consume the matrix stage's results:
+    Distance_Decay (:201-272) with its own gap rule and with a given gap list, the O/E loop of Get_PCA (:318-326),
+    Get_DI (:804-840) in both flavours, bias_handle (:1948-1952)."""
+    sf = ref_shim.load_structure()
+    obj = object.__new__(sf.StructureFind)
+    rng = np.random.default_rng(99)
+    n = 120
+    bias = np.exp(rng.normal(0, 0.3, n))
+    d = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) + 1.0
+    M = rng.poisson(40.0 * bias[:, None] * bias[None, :] / d).astype(float)
+    M = np.triu(M) + np.triu(M, 1).T
+    M[30:34, :] = 0; M[:, 30:34] = 0; M[77, :] = 0; M[:, 77] = 0
+    w = 1.0 / np.sqrt(np.maximum(M.sum(1), 1.0)); w[[30, 31, 32, 33, 77]] = np.nan
+    cM = np.nan_to_num(M * w[:, None] * w[None, :])            # what cooler hands CallPeaks (:2005-2007)
+    out = {"M": M, "weight": w, "cM": cM}
+    db, G, NG = obj.Distance_Decay(cM, None)
+    out.update(dd_auto=db.copy(), dd_auto_G=np.asarray(G), dd_auto_NG=np.asarray(NG))
+    given = np.array([3, 30, 31, 32, 33, 77, 119]).view(_GapArray)
+    db2, G2, NG2 = obj.Distance_Decay(cM, given)
+    out.update(dd_given=db2.copy(), dd_given_G=np.asarray(G2), dd_given_NG=np.asarray(NG2))
+    # the O/E loop of Get_PCA, verbatim semantics (:318-326); the PCA that follows is outside the scope
+    decline = db.copy()
+    decline[decline == 0] = decline[np.nonzero(decline)].min()
+    OE = np.zeros(cM.shape)
+    for i in range(n):
+        for j in range(n):
+            if cM[i][j] != 0:
+                OE[i][j] = cM[i][j] / decline[abs(i - j)]
+    out["OE"] = OE
+    window = rng.integers(1, 9, n)
+    gap = np.array([30, 31, 32, 33, 77])
+    for t in ("ttest", "chitest"):
+        obj.test_type = t
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out["DI_" + t] = obj.Get_DI(cM, gap, window)
+    out.update(window=window, gap=gap)
+    b = w.copy().reshape(-1, 1)
+    out["bias_handled"] = obj.bias_handle(b.copy())
+    np.savez_compressed(os.path.join(GOLDEN, "consumers.npz"), **out)
+    return out
+
+
 def make_ice_restated(trad):
     """Regression anchor for the cooler restatement (NOT a reference output)."""
     out = {}
@@ -302,6 +358,7 @@ def main():
     make_imputation()
     make_twostep_cases()
     make_building_blocks()
+    make_consumers()
     make_ice_restated(trad)
     for f in sorted(os.listdir(GOLDEN)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(GOLDEN, f))))

@@ -83,3 +83,56 @@ def load():
     exec(compile(src, _REF_FILE, "exec"), mod.__dict__)
     _cached = mod
     return mod
+
+
+_REF_SF = os.path.join(REFERENCE_ROOT, "HiCHap", "StructureFind.py")
+_cached_sf = None
+
+
+def load_structure():
+    """The reference ``StructureFind`` module (HiCHap/StructureFind.py), unmodified except for the Python-2 surface:
+    ``print x`` statements, ``xrange``, and stub modules for imports that are absent here (matplotlib, statsmodels,
+    ghmm, cooler) -- none of them is touched by the methods the goldens use (Distance_Decay, Get_PCA's O/E loop,
+    Get_DI, bias_handle)."""
+    global _cached_sf
+    if _cached_sf is not None:
+        return _cached_sf
+    if not os.path.isfile(_REF_SF):
+        raise FileNotFoundError(_REF_SF)
+    import numpy as np
+    for name, typ in (("int", int), ("float", float), ("bool", bool)):
+        if not hasattr(np, name):
+            setattr(np, name, typ)
+    try:
+        import cooler  # noqa: F401
+    except Exception:
+        _install_cooler_stubs()
+
+    def stub(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        m._hc_stub = True
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    na = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stubbed import"))
+    mpl = stub("matplotlib", use=lambda *a, **k: None)
+    stub("matplotlib.backends")
+    stub("matplotlib.backends.backend_pdf", PdfPages=na)
+    stub("matplotlib.colors", LinearSegmentedColormap=na)
+    mpl.pyplot = stub("matplotlib.pyplot")
+    stub("statsmodels"); stub("statsmodels.sandbox"); stub("statsmodels.sandbox.stats")
+    stub("statsmodels.sandbox.stats.multicomp", multipletests=na)
+    stub("ghmm")
+    with open(_REF_SF, "r") as fh:
+        src = fh.read()
+    src = re.sub(r"^(\s*)print (.+)$", r"\1print(\2)", src, flags=re.M)
+    mod = types.ModuleType("hichap_reference_StructureFind")
+    mod.__file__ = _REF_SF
+    mod.__dict__["xrange"] = range
+    exec(compile(src, _REF_SF, "exec"), mod.__dict__)
+    _cached_sf = mod
+    return mod

@@ -224,3 +224,19 @@ def test_building_blocks_golden():
         np.testing.assert_allclose(ho.correct_vc(g[tag + "|Sym"], 2.0 / 3), g[tag + "|VC"], rtol=1e-13)
     np.testing.assert_allclose(ho.trans2symmetry(g["forced|S"], g["forced|Gap"]), g["forced|Sym"], rtol=1e-14)
     np.testing.assert_allclose(ho.correct_vc(g["rect|X"], 0.5), g["rect|VC"], rtol=1e-13)
+
+
+def test_consumers_golden():
+    """oracle restatements of StructureFind's first consumers of the stage outputs vs the reference's own methods
+    (Distance_Decay :201-272, the O/E loop of Get_PCA :318-326, Get_DI :804-840)."""
+    g = load_golden("consumers.npz")
+    np.testing.assert_array_equal(ho.balanced_matrix(g["M"], g["weight"]), g["cM"])
+    db, G, NG = ho.distance_decay(g["cM"], None)
+    np.testing.assert_allclose(db, g["dd_auto"], rtol=1e-13)
+    assert np.array_equal(G, g["dd_auto_G"]) and np.array_equal(NG, g["dd_auto_NG"])
+    db, G, NG = ho.distance_decay(g["cM"], g["dd_given_G"])
+    np.testing.assert_allclose(db, g["dd_given"], rtol=1e-13)
+    assert np.array_equal(NG, g["dd_given_NG"])
+    np.testing.assert_allclose(ho.observed_expected(g["cM"], g["dd_auto"]), g["OE"], rtol=1e-13)
+    for t in ("ttest", "chitest"):
+        np.testing.assert_allclose(ho.get_di(g["cM"], g["gap"], g["window"], t), g["DI_" + t], rtol=1e-12, equal_nan=True)
