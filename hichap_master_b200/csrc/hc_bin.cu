@@ -7,6 +7,8 @@
 // Roofline: HBM-bound streaming read of the columnar pairs (16 B/pair, +1 B mark) with 128-bit
 // loads; the += 1 updates are 32-bit RED atomics resolved in L2 (not HBM traffic).
 #include <algorithm>
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "hc_common.cuh"
 
 namespace {
@@ -230,6 +232,102 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_band_kernel(BandArgs a)
     }
 }
 
+// ---- cluster variant: the hottest diagonals are counted in DISTRIBUTED SHARED MEMORY ---------------------------
+// The banded kernel above is bound by the L2 atomic rate (~80 G RED/s measured: 400 M pairs = 5 ms).  Half of all
+// Hi-C pairs fall on the first few diagonals (P(s) ~ 1/s), so a thread-block cluster keeps 16-bit counters for the
+// diagonals d < d_hot of EVERY bin in the shared memory of its CTAs (cluster of 8 x 200 KB = 800 K counters = 10
+// diagonals of the 75 918 bins of hg19 at 40 kb): a pair on a hot diagonal becomes one shared-memory atomic on the
+// CTA that owns the counter (distributed shared memory), and only the other pairs go to L2 (band) / DRAM (far
+// pairs).  At the end of the launch every CTA adds its non-zero counters into the band.  A counter that reaches
+// 0x8000 is drained into the band by the thread that saw it cross (at most 8 x 1024 threads can add in between, so the
+// 16-bit field never carries into its neighbour).
+constexpr int HOT_THREADS = 1024;
+constexpr int HOT_PER_CTA = 100 * 1024;          // 16-bit counters per CTA (200 KB of shared memory)
+constexpr int HOT_MAX_D = 16;
+
+template <bool U8>
+__global__ void __launch_bounds__(HOT_THREADS, 1) bin_pairs_band_cluster_kernel(BandArgs a) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) uint32_t hot[];          // HOT_PER_CTA / 2 words
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const long long nbins = a.bin_off[a.nchrom];
+    const int d_hot = (int)min((long long)HOT_MAX_D, nbins > 0 ? (long long)csize * HOT_PER_CTA / nbins : 0ll);
+    for (int i = threadIdx.x; i < HOT_PER_CTA / 2; i += blockDim.x) hot[i] = 0u;
+    cluster.sync();
+    const int64_t nvec = a.npairs / PAIRS_PER_THREAD;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long my_oob = 0;
+    const uint64_t once = l2_policy_evict_first(), keep = l2_policy_evict_last();
+    const uint8_t* c1b = reinterpret_cast<const uint8_t*>(a.in.c1);
+    const uint8_t* c2b = reinterpret_cast<const uint8_t*>(a.in.c2);
+    auto apply = [&](int c1, int p1, int c2, int p2, int mk) {
+        if (c1 < 0 || c1 != c2 || c1 >= a.nchrom) return;
+        if (!mode_accepts(a.mode, mk)) return;
+        if (p1 < 0 || p2 < 0) { ++my_oob; return; }
+        const uint32_t b1 = fast_div((uint32_t)p1, a.res), b2 = fast_div((uint32_t)p2, a.res), n = (uint32_t)a.mat_n[c1];
+        if (b1 >= n || b2 >= n) { ++my_oob; return; }
+        const uint32_t lo = min(b1, b2), d = max(b1, b2) - lo;
+        const long long grow = a.bin_off[c1] + lo;
+        if ((int)d < d_hot) {
+            const unsigned idx = (unsigned)(grow * d_hot + d);
+            const unsigned owner = idx / HOT_PER_CTA, local = idx - owner * HOT_PER_CTA;
+            uint32_t* w = cluster.map_shared_rank(hot, owner) + (local >> 1);
+            const unsigned sh = (local & 1u) * 16u;
+            const uint32_t old = atomicAdd(w, 1u << sh);
+            if (((old >> sh) & 0xffffu) == 0x7fffu) {          // this add made it 0x8000: drain that much into the band
+                atomicSub(w, 0x8000u << sh);
+                red_add_s32_hint(a.band + ((grow << a.bw_shift) + d), 0x8000, keep);
+            }
+        } else if ((d >> a.bw_shift) == 0) red_add_s32_hint(a.band + ((grow << a.bw_shift) + d), 1, keep);
+        else atomicAdd(a.mats + a.mat_off[c1] + (int64_t)lo * a.mat_ld[c1] + (lo + d), 1);
+    };
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        int4 c1, c2;
+        if (U8) {
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(c1b + 4 * v), w2 = *reinterpret_cast<const uint32_t*>(c2b + 4 * v);
+            c1 = make_int4(w1 & 255, (w1 >> 8) & 255, (w1 >> 16) & 255, w1 >> 24);
+            c2 = make_int4(w2 & 255, (w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+        } else {
+            c1 = ld_stream_v4_hint(a.in.c1 + 4 * v, once);
+            c2 = ld_stream_v4_hint(a.in.c2 + 4 * v, once);
+        }
+        const int4 p1 = ld_stream_v4_hint(a.in.p1 + 4 * v, once), p2 = ld_stream_v4_hint(a.in.p2 + 4 * v, once);
+        uint32_t mk = 0;
+        if (a.in.mark) mk = *reinterpret_cast<const uint32_t*>(a.in.mark + 4 * v);
+        apply(c1.x, p1.x, c2.x, p2.x, mk & 255);
+        apply(c1.y, p1.y, c2.y, p2.y, (mk >> 8) & 255);
+        apply(c1.z, p1.z, c2.z, p2.z, (mk >> 16) & 255);
+        apply(c1.w, p1.w, c2.w, p2.w, (mk >> 24) & 255);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(a.npairs - nvec * PAIRS_PER_THREAD)) {
+        const int64_t i = nvec * PAIRS_PER_THREAD + threadIdx.x;
+        const int x = U8 ? (int)c1b[i] : a.in.c1[i], y = U8 ? (int)c2b[i] : a.in.c2[i];
+        apply(x, a.in.p1[i], y, a.in.p2[i], a.in.mark ? a.in.mark[i] : 0);
+    }
+    cluster.sync();            // every remote add has landed; nobody touches this CTA's counters any more
+    if (d_hot > 0) {
+        for (int i = threadIdx.x; i < HOT_PER_CTA / 2; i += blockDim.x) {
+            const uint32_t w = hot[i];
+            if (w == 0u) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int v = (int)((w >> (16 * h)) & 0xffffu);
+                if (v) {
+                    const unsigned idx = crank * HOT_PER_CTA + 2u * i + h;
+                    const long long grow = idx / d_hot;
+                    const int d = (int)(idx - grow * d_hot);
+                    if (grow < nbins) red_add_s32_hint(a.band + ((grow << a.bw_shift) + d), v, keep);
+                }
+            }
+        }
+    }
+    if (a.oob) {
+        my_oob = (unsigned long long)warp_sum_ll((long long)my_oob);
+        if ((threadIdx.x & 31) == 0 && my_oob) atomicAdd(a.oob, my_oob);
+    }
+}
+
 // tiles[r][r + d] += band[r][d]: one warp per global row, coalesced on both sides
 __global__ void __launch_bounds__(256) band_merge_kernel(BandArgs a, int64_t nbins) {
     const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -418,6 +516,28 @@ extern "C" int hc_bin_band_accumulate(const void* c1, const int32_t* p1, const v
     a.nchrom = nchrom; a.mats = mats; a.mat_off = mat_off; a.mat_n = mat_n; a.mat_ld = mat_ld; a.bin_off = bin_off;
     a.band = reinterpret_cast<int32_t*>(work); a.oob = oob;
     a.bw_shift = band_shift(band_width);
+    // HC_BIN_CLUSTER=N (N = 2, 4, 8 or 16): the hottest diagonals are counted in the distributed shared memory of
+    // clusters of N CTAs (bin_pairs_band_cluster_kernel); 0 = every near-diagonal update is an L2 RED
+    int csize = 0;
+    if (const char* e = getenv("HC_BIN_CLUSTER")) csize = atoi(e);
+    if (csize >= 2 && csize <= 16 && (csize & (csize - 1)) == 0 && npairs >= (1 << 20)) {
+        auto kern = chrom_is_u8 ? bin_pairs_band_cluster_kernel<true> : bin_pairs_band_cluster_kernel<false>;
+        const size_t smem = (size_t)HOT_PER_CTA * 2;
+        HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (csize > 8) HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(hc_num_sms() / csize * csize));      // one CTA per SM, whole clusters
+        cfg.blockDim = dim3(HOT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        HC_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+        HC_LAUNCH_CHECK();
+        return HC_OK;
+    }
     if (chrom_is_u8) bin_pairs_band_kernel<true><<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
     else bin_pairs_band_kernel<false><<<bin_grid(npairs), BIN_THREADS, 0, s>>>(a);
     HC_LAUNCH_CHECK();

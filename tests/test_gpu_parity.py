@@ -488,6 +488,40 @@ def test_banded_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
         kernels.bin_pairs_local_banded(bad, res, DenseBatch(sizes, cuda_device))
 
 
+@pytest.mark.parametrize("csize,pile", [("8", False), ("4", True), ("16", False), ("2", True)])
+def test_cluster_binning_equals_direct(mb, cuda_device, monkeypatch, csize, pile):
+    """HC_BIN_CLUSTER=N: the hottest diagonals are counted in the distributed shared memory of N-CTA clusters
+    (16-bit counters, drained into the band when they reach 0x8000).  `pile`: 200 000 pairs in ONE cell, several
+    times the 16-bit drain threshold."""
+    import torch
+    from hichap_master_b200 import kernels
+    from hichap_master_b200.device import DenseBatch, PairColumns
+    genome = {c: l for c, l in SMALL_GENOME.items() if c != "M"}
+    order = list(genome)
+    res = 40000
+    c1, p1, c2, p2 = synth.genome_pairs(genome, order, 1_400_000, 91, trans_frac=0.1)
+    if pile:
+        c1[:200_000] = 1; c2[:200_000] = 1; p1[:200_000] = 1_234_567; p2[:200_000] = 1_240_000
+        c1[200_000:260_000] = 2; c2[200_000:260_000] = 2; p1[200_000:260_000] = 40_000 * 7; p2[200_000:260_000] = 40_000 * 8 + 5
+    sizes = [genome[c] // res + 1 for c in order]
+    pc = PairColumns(c1, p1, c2, p2)
+    A = DenseBatch(sizes, cuda_device); B = DenseBatch(sizes, cuda_device)
+    kernels.bin_pairs_local(pc, res, A)
+    monkeypatch.setenv("HC_BIN_CLUSTER", csize)
+    kernels.bin_pairs_local_banded(pc, res, B)
+    assert torch.equal(A.buf, B.buf)
+    # uint8 chromosome columns, fed in two chunks (the PCIe-overlapped path)
+    Cb = DenseBatch(sizes, cuda_device)
+    bb = kernels.BandedBinning(Cb, res)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(cuda_device)
+    u1 = np.where(c1 < 0, 255, c1).astype(np.uint8); u2 = np.where(c2 < 0, 255, c2).astype(np.uint8)
+    h = 1_100_000 // 16 * 16
+    for sl in (slice(0, h), slice(h, None)):
+        bb.accumulate(t(u1[sl], np.uint8), t(p1[sl], np.int32), t(u2[sl], np.uint8), t(p2[sl], np.int32))
+    bb.finish()
+    assert torch.equal(A.buf, Cb.buf)
+
+
 @pytest.mark.parametrize("n,chunk", [(0, 64), (5, 16), (100_003, 4096), (100_003, 1 << 24)])
 def test_stage_from_host_chunks_equals_whole_upload(mb, cuda_device, n, chunk):
     """`LocalStage.run_from_host` (chunked H2D on a copy stream, uint8 chromosome columns binned as
