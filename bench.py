@@ -369,8 +369,12 @@ def run_ours(args):
     del stage, out, o2
     torch.cuda.empty_cache()
 
+    c1 = c3 = None
     if rank == 0 and not args.skip_secondary:
         secondary.append(twostep_roofline(dev, peak, ev_time))
+        if world == 1:          # the other single-GPU configs of BASELINE.json, at their stated sizes
+            c1 = c1_section(dev)
+            c3 = c3_section(100_000_000, dev, peak)
     c4 = None
     if not args.skip_c4:
         c4 = run_c4_section(args, world, rank, dev, peak)
@@ -448,12 +452,17 @@ def run_ours(args):
         line["parity_check"] = parity
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if c1 is not None:
+        line["c1"] = c1
+    if c3 is not None:
+        line["c3"] = c3
     if c4 is not None:
         line["c4"] = c4
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    bad = (parity is not None and not parity["ok"]) or (c4 is not None and c4.get("parity_check") and not c4["parity_check"]["ok"])
+    bad = ((parity is not None and not parity["ok"]) or (c4 is not None and c4.get("parity_check") and not c4["parity_check"]["ok"])
+           or (c1 is not None and not c1["parity_check"]["ok"]))
     if bad:
         sys.stderr.write("bench.py: PARITY CHECK FAILED (see parity_check in the line above)\n")
         sys.exit(3)
@@ -733,20 +742,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_c3(args):
-    """--config C3 (BASELINE.json configs[2]): allelic maternal/paternal matrices at 40 kb with the
-    two-step (ICE of the traditional matrices + SNP-density / coverage) correction.  Single GPU;
-    prints one JSON line with the stage breakdown."""
+def c3_section(pairs_n, dev, peak):
+    """BASELINE.json configs[2] (C3): allelic maternal/paternal matrices at 40 kb with the two-step (ICE of the
+    traditional matrices + SNP-density / coverage) correction.  Single GPU; returns the stage breakdown."""
     import torch
-    from hichap_master_b200 import _abi, kernels, matrixBuilding as mb, synth
+    from hichap_master_b200 import _abi, kernels, synth
     from hichap_master_b200.construction import _sub_batch
     from hichap_master_b200.device import DenseBatch, PairColumns
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
     genome, order = c2_genome()
     nchrom = len(order)
-    pairs_n = args.pairs if args.pairs != 400_000_000 else 100_000_000
     c1, p1, c2, p2 = synth.genome_pairs_torch(genome, order, pairs_n, 3, dev, trans_frac=0.0)
     g = torch.Generator(device=dev); g.manual_seed(33)
     cls = torch.rand(pairs_n, generator=g, device=dev)          # Bi 86 %, M_M 6 %, P_P 6 %, M_P 1 %, P_M 1 %
@@ -756,6 +761,7 @@ def run_c3(args):
     for lo, hi in ((0.86, 0.92), (0.92, 0.98)):
         sel = (cls >= lo) & (cls < hi)
         hap.append(PairColumns(c1[sel], p1[sel], c2[sel], p2[sel], mark[sel], device=dev))
+    del cls, mark
     sizes = [genome[c] // RES + 1 for c in order]
     T = DenseBatch(sizes, dev)
     H = DenseBatch(sizes + sizes, dev)
@@ -774,22 +780,70 @@ def run_c3(args):
             kernels.bin_pairs_local(hap[k], RES, v, _abi.HC_BIN_SYM_BOTH, check_bounds=False)
             kernels.bin_pairs_local(hap[k], RES, v, _abi.HC_BIN_ONESIDED, check_bounds=False)
 
-    def correct_all():
-        return kernels.twostep_batch(T, H)
-
     res_t, outs = {}, None
-    for rep in range(4):                         # first pass warms the allocator; report the last
+    for rep in range(3):                         # first pass warms the allocator; report the last
         outs = None                              # release the 4.7 GB of corrected matrices before re-allocating
         res_t["binning_ms"], _ = ev(bin_all)
         res_t["ice_traditional_ms"], (w, st) = ev(lambda: kernels.ice_balance_dense(T, None, ignore_diags=1))
-        res_t["two_step_ms"], outs = ev(correct_all)
+        res_t["two_step_ms"], outs = ev(lambda: kernels.twostep_batch(T, H))
     sq = float(sum(n * n for n in sizes))
-    print(json.dumps({
-        "config": {"workload": "C3: hg19 chr1-22,X allelic matrices at 40 kb, %d synthetic pairs (86%% bi-allelic, 6%% M_M, 6%% P_P; "
-                               "Both/R1/R2 = 30/35/35%%), ICE of the traditional matrices + two-step correction of M and P" % pairs_n},
-        "n_gpus": 1, **res_t, "total_ms": sum(res_t.values()), "ice_iters_max": int(max(st["iters"])),
-        "two_step_algorithmic_GBps": 52.0 * sq / (res_t["two_step_ms"] * 1e6),
-        "gap_rows_total": int(sum(g.size for g in outs[1]))}))
+    gaps = int(sum(g.size for g in outs[1]))
+    del outs, T, H, allp, hap
+    torch.cuda.empty_cache()
+    return {"workload": "C3: hg19 chr1-22,X allelic matrices at 40 kb, %d synthetic pairs (86%% bi-allelic, 6%% M_M, 6%% P_P; "
+                        "Both/R1/R2 = 30/35/35%%), ICE of the traditional matrices + two-step correction of M and P" % pairs_n,
+            "n_gpus": 1, **res_t, "total_ms": sum(res_t.values()), "ice_iters_max": int(max(st["iters"])),
+            "two_step_roofline": {"formula": "52*N^2 summed over the chromosomes (SURVEY 8d)", "algorithmic_bytes": 52.0 * sq,
+                                  "achieved": 52.0 * sq / (res_t["two_step_ms"] * 1e6), "peak": peak,
+                                  "frac": 52.0 * sq / (res_t["two_step_ms"] * 1e6) / peak, "unit": "GB/s"},
+            "gap_rows_total": gaps}
+
+
+def c1_section(dev, pairs_n=10_000_000):
+    """BASELINE.json configs[0] (C1): chr21 only, 40 kb, 10 M cis pairs: binning + ICE, checked against the oracle."""
+    import torch
+    from hichap_master_b200 import kernels, synth
+    from hichap_master_b200.device import DenseBatch, PairColumns
+    from oracle import cooler_ice, hichap_oracle as ho
+    L = synth.HG19["21"]
+    n = L // RES + 1
+    _, a, _, b = synth.genome_pairs_torch({"21": L}, ["21"], pairs_n, 1, dev)
+    z = torch.zeros_like(a)
+    pairs = PairColumns(z, a, z, b, device=dev)
+    batch = DenseBatch([n], dev)
+
+    def step():
+        batch.buf.zero_()
+        kernels.bin_pairs_local_banded(pairs, RES, batch, check_bounds=False)
+        return kernels.ice_balance_dense(batch, None, ignore_diags=1)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        w, st = step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    t0 = time.perf_counter()
+    hz = np.zeros(pairs_n, np.int32)
+    M = ho.bin_local_dense(hz, a.cpu().numpy(), hz, b.cpu().numpy(), [n], RES)[0]
+    ref, rst = cooler_ice.balance_dense(M, cis_only=True)
+    cpu_s = time.perf_counter() - t0
+    ok = ~np.isnan(ref)
+    err = float(np.max(np.abs(w[ok] - ref[ok]) / np.abs(ref[ok])))
+    return {"workload": "C1: chr21 (-C 21), 40 kb, 1204 bins, %d synthetic cis pairs, binning + ICE to convergence" % pairs_n,
+            "ms_per_step": ms, "iters": int(st["iters"][0]), "cpu_port_one_core_ms": cpu_s * 1e3,
+            "parity_check": {"ok": bool(np.array_equal(batch.to_numpy(0), M) and np.array_equal(np.isnan(w), np.isnan(ref))
+                                        and st["iters"][0] == rst["iters"][0] and err < RTOL),
+                             "counts_equal": bool(np.array_equal(batch.to_numpy(0), M)), "iters_oracle": int(rst["iters"][0]), "max_rel_err": err}}
+
+
+def run_c3(args):
+    import torch
+    torch.cuda.set_device(0)
+    peak = float(load_peaks().get("hbm_gbs", 6650.0))
+    print(json.dumps(c3_section(args.pairs if args.pairs != 400_000_000 else 100_000_000, torch.device("cuda", 0), peak)))
 
 
 def main():
