@@ -68,6 +68,7 @@ struct SymTables {              // per chromosome, device
     const int32_t* blk_off;     // offset of the chromosome's per-block bookkeeping
     const int32_t* item_first;  // [nprob + 1] prefix of items
     const int32_t* prio;        // chromosomes, largest first (order of the ticket scan)
+    const int32_t* rank_of;     // inverse of prio
     const int64_t* bin_off;     // concatenated (unpadded) bins (the caller's table)
 };
 
@@ -191,6 +192,7 @@ struct SymArgs {
     int32_t* dig_exp;
     double* part;                               // per chromosome: nblk planes of row partials, then nblk planes of column partials
     int32_t* tick; int32_t* blkdone; int32_t* adone; int32_t* iters; int32_t* n_active;
+    unsigned long long* avail;                  // bit r: the chromosome of priority rank r has tickets left this iteration
     int32_t* abort_flag;                        // set by a CTA that waited implausibly long for work (dataflow bug guard)
     long long spin_limit;                       // clock64 ticks a CTA may wait for work before it raises abort_flag
     double* blk_sum; long long* blk_cnt;        // per block: sum / count of the non-zero marginals (phase A -> phase B)
@@ -233,54 +235,40 @@ __device__ __forceinline__ double block_max_sym(double v, double* red) {
     return t;
 }
 
-// Warp-collective (warp 0): draw a block of some chromosome that has one.  Fast path: the chromosome the last ticket came
-// from (one atomic round trip); otherwise the lanes read the ticket counters of the chromosomes in priority order
-// (largest first: the largest chromosome is the critical path) in parallel and the first one with tickets left is tried.
-// Returns the item index or -1 (nothing available right now); *hint = rank of the chromosome that served.
-__device__ __forceinline__ int sym_try_acquire(const SymArgs& A, int* hint) {
-    const int lane = threadIdx.x & 31;
-    int item = -1;
-    if (lane == 0 && *hint >= 0) {
-        const int p = A.T.prio[*hint];
-        const int n = A.T.item_first[p + 1] - A.T.item_first[p];
-        if (ld_volatile_i32(A.tick + p) < n) {
-            const int t = atomicAdd(A.tick + p, 1);
-            if (t < n) item = A.T.item_first[p] + t;
-        }
-    }
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= 0) return item;
-    for (int r0 = 0; r0 < A.nprob; r0 += 32) {
-        const int r = r0 + lane;
-        int avail = 0, p = 0, n = 0;
-        if (r < A.nprob) {
-            p = A.T.prio[r];
-            n = A.T.item_first[p + 1] - A.T.item_first[p];
-            avail = ld_volatile_i32(A.tick + p) < n;
-        }
-        unsigned m = __ballot_sync(0xffffffffu, avail);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            if (lane == src) {
-                const int t = atomicAdd(A.tick + p, 1);
-                if (t < n) item = A.T.item_first[p] + t;
-            }
-            item = __shfl_sync(0xffffffffu, item, src);
-            if (item >= 0) { *hint = r0 + src; return item; }
-            m &= m - 1;
-        }
-    }
-    return -1;
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
 }
 
-// lane 0 of warp 0: start the bulk copy of a block into a buffer
+// thread 0: start the bulk copies of a block (64 KB of tiles) and of the bias byte planes of its columns (dig1, 2 KB)
+// and rows (dig2, 2 KB) into a buffer; all three complete on the buffer's mbarrier.  The planes were written by the
+// phase B that re-opened the chromosome's tickets, i.e. before this block's ticket could be drawn.
+constexpr int DIG_BYTES = 8 * 256;                          // 8 k-tiles (or strip pairs) x 256 B
+constexpr int BUF_BYTES = BLK_BYTES + 2 * DIG_BYTES;
 __device__ __forceinline__ void sym_issue_copy(const SymArgs& A, int item, unsigned char* buf, unsigned long long* bar) {
     const int4 d = __ldg(A.items + item);
     const long long off = ((long long)(uint32_t)d.x) | ((long long)d.y << 32);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic-proxy reads of buf precede the async write
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"((uint32_t)BLK_BYTES) : "memory");
+    const int p = d.z, I = d.w & 0xffff, J = d.w >> 16;
+    const int64_t lo = A.T.pad_off[p];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic-proxy reads of buf precede the async writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"((uint32_t)BUF_BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(buf)), "l"(A.q8 + off), "r"((uint32_t)BLK_BYTES), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(buf + BLK_BYTES)), "l"(A.dig1 + 8 * lo + (int64_t)(8 * J) * 256), "r"((uint32_t)DIG_BYTES), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(buf + BLK_BYTES + DIG_BYTES)), "l"(A.dig2 + 8 * lo + (int64_t)(8 * I) * 256), "r"((uint32_t)DIG_BYTES), "r"(smem_u32(bar)) : "memory");
+}
+
+// thread 0: turn a drawn ticket into an item (or -1).  The drawer of a chromosome's LAST ticket clears its bit in the
+// availability mask -- that happens before the block's completion, hence before the phase B that sets the bit again.
+__device__ __forceinline__ int sym_ticket_item(const SymArgs& A, int r, int t) {
+    const int p = A.T.prio[r];
+    const int n = A.T.item_first[p + 1] - A.T.item_first[p];
+    if (t >= n) return -1;
+    if (t == n - 1) atomicAnd(A.avail, ~(1ull << r));
+    return A.T.item_first[p] + t;
 }
 
 // byte planes of 4 consecutive bins j4 .. j4+3 (fixed point F = round(b * 2^(64 - E)), plane 0 most significant):
@@ -421,7 +409,7 @@ __device__ void sym_phase_b(const SymArgs& A, int p, double* red, long long* red
         A.adone[p] = 0;
         __threadfence();
         if (finished) atomicSub(A.n_active, 1);
-        else atomicExch(A.tick + p, 0);
+        else { atomicExch(A.tick + p, 0); __threadfence(); atomicOr(A.avail, 1ull << A.T.rank_of[p]); }
     }
 }
 
@@ -442,208 +430,215 @@ __device__ void sym_phases(const SymArgs& A, int p, int I, int J, int fi, int fj
 
 constexpr int NBUF = 3;
 
+// The persistent kernel.  One CTA per SM; every CTA runs the loop
+//     [B0] -> phases the previous blocks made this CTA responsible for (rare) -> block of slot s: wait for its bulk
+//     copy, both integer products, plane sums -> fp64 -> [B1] -> partial sums to global -> [B2] -> thread 0: fence,
+//     completion counters
+// with everything that needs a round trip to L2 issued one block ahead of its use by thread 0: the ticket atomic
+// and the availability mask are requested in block k and looked at in block k + 1 (the drawn block then gets its bulk
+// copies, two blocks before it is processed); the completion counters bumped after block k are looked at after block
+// k + 1.  So the critical path of a block is the shared-memory work plus three CTA barriers.
 __global__ void __launch_bounds__(SYM_THREADS, 1)
 sym_ice_kernel(SymArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double* red_r = reinterpret_cast<double*>(smem_raw + NBUF * BLK_BYTES);   // [4][256]
+    double* red_r = reinterpret_cast<double*>(smem_raw + NBUF * BUF_BYTES);   // [4][256]
     double* red_c = red_r + 4 * BLK;                                           // [4][256]
     __shared__ __align__(8) unsigned long long bar[NBUF];
     __shared__ double red[32];
     __shared__ long long redll[32];
-    __shared__ int sh_q[NBUF];          // items in hand: sh_q[0] is processed next, the others are being prefetched
-    __shared__ int sh_flag[8];          // resolved completion of the previous item: valid, p, I, J, fi, fj; [6] = last; [7] = exit
+    __shared__ int sh_item[NBUF];       // block held by each buffer (-1 = none)
+    __shared__ int sh_flag[8];          // resolved completion of an earlier block: valid, p, I, J, fi, fj; [6] = last
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp >> 2, wj = warp & 3;
     const int g = lane >> 2, q = lane & 3;
     const double w_even = __longlong_as_double((long long)(1023 + 8 * (7 - 2 * q)) << 52);
     const double w_odd = __longlong_as_double((long long)(1023 + 8 * (6 - 2 * q)) << 52);
-    int hint = -1;                      // warp 0: rank of the chromosome that served the last ticket
-    int b0 = 0;                         // buffer of sh_q[0]; slot s uses buffer (b0 + s) % NBUF
     uint32_t phasebits = 0u;            // expected parity of each buffer's mbarrier
-    // thread 0: completion of the previous item, issued but not yet looked at
+    // thread 0 only: the outstanding ticket, the last availability mask seen, the completion counters not yet looked at
+    int tk_valid = 0, tk_r = 0, tk_t = 0;
+    unsigned long long mask_seen = 0ull;
     int pend_valid = 0, pend_p = 0, pend_I = 0, pend_J = 0, pend_oldI = 0, pend_oldJ = 0;
     if (tid == 0) {
-        for (int x = 0; x < NBUF; ++x)
+        for (int x = 0; x < NBUF; ++x) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[x])), "r"(1) : "memory");
+            sh_item[x] = -1;
+        }
+        sh_flag[0] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == 0) {
-        for (int x = 0; x < NBUF; ++x) {
-            const int it = sym_try_acquire(A, &hint);
-            if (lane == 0) {
-                sh_q[x] = it;
-                if (it >= 0) { __threadfence(); sym_issue_copy(A, it, smem_raw + x * BLK_BYTES, &bar[x]); }
-            }
+    auto resolve_pending = [&]() {      // thread 0: did the block before last complete a block index?
+        sh_flag[0] = 0;
+        if (pend_valid) {
+            const int need = A.T.nblk[pend_p] + 1;
+            const int fi = pend_I == pend_J ? (pend_oldI + 2 == need) : (pend_oldI + 1 == need);
+            const int fj = pend_I == pend_J ? 0 : (pend_oldJ + 1 == need);
+            if (fi || fj) { sh_flag[0] = 1; sh_flag[1] = pend_p; sh_flag[2] = pend_I; sh_flag[3] = pend_J; sh_flag[4] = fi; sh_flag[5] = fj; }
+            pend_valid = 0;
         }
-    }
-    __syncthreads();
-    for (;;) {
-        int cur = sh_q[0];
-        // warp 0: keep the prefetch slots full (one attempt per empty slot: nothing may be available right now)
-        if (warp == 0) {
-            for (int x = 1; x < NBUF && cur >= 0; ++x) {
-                if (sh_q[x] >= 0) continue;
-                const int it = sym_try_acquire(A, &hint);
-                if (it < 0) break;          // slots fill in order: a later slot never holds a block while an earlier one is empty
-                if (lane == 0) {
-                    sh_q[x] = it;
-                    __threadfence();
-                    sym_issue_copy(A, it, smem_raw + ((b0 + x) % NBUF) * BLK_BYTES, &bar[(b0 + x) % NBUF]);
-                }
-                __syncwarp();
+    };
+    for (int it = 0;; ++it) {
+        const int s = it % NBUF;
+        __syncthreads();                                                          // [B0]
+        if (sh_flag[0]) sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
+        int cur = sh_item[s];
+        if (cur < 0) {
+            // Nothing in hand (then no buffer holds a block: they fill in order).  Settle what is outstanding, then wait for
+            // work or for the end.
+            __syncthreads();
+            if (tid == 0) resolve_pending();
+            __syncthreads();
+            if (sh_flag[0]) {
+                sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
+                if (tid == 0) sh_flag[0] = 0;
             }
-        }
-        if (cur >= 0) {
-            const int4 d = __ldg(A.items + cur);
-            const int p = d.z, I = d.w & 0xffff, J = d.w >> 16;
-            const int nblk = A.T.nblk[p];
-            const int64_t lo = A.T.pad_off[p], npad = (int64_t)nblk * BLK;
-            // bias planes of this block's columns (product 1) and rows (product 2): rewritten every iteration by another
-            // SM, so they bypass L1
-            uint2 bf1[2], bf2[2];
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt) bf1[kt] = ldcg_u2(A.dig1 + 8 * lo + (int64_t)(8 * J + 2 * wj + kt) * 256 + 8 * lane);
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) bf2[sp] = ldcg_u2(A.dig2 + 8 * lo + (int64_t)(8 * I + 2 * wi + sp) * 256 + 8 * lane);
-            const double scale = __longlong_as_double((long long)(1023 + __ldcg(A.dig_exp + p) - 64) << 52);   // 2^(E - 64)
-            {                               // wait for the block to land
-                const uint32_t par = (phasebits >> b0) & 1u;
-                uint32_t done = 0;
-                while (!done) {
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                                 : "=r"(done) : "r"(smem_u32(&bar[b0])), "r"(par) : "memory");
-                }
-                phasebits ^= 1u << b0;
-            }
-            const uint32_t base = smem_u32(smem_raw + b0 * BLK_BYTES);
-            int c1[4][4], c2[2][2][4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { c1[s][0] = 0; c1[s][1] = 0; c1[s][2] = 0; c1[s][3] = 0; }
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) { c2[kt][h][0] = 0; c2[kt][h][1] = 0; c2[kt][h][2] = 0; c2[kt][h][3] = 0; }
-            const int mj = lane >> 3, mi = lane & 7;         // ldmatrix.trans: lane supplies row mi of matrix mj
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
-                    const uint32_t tileA = base + (uint32_t)(((4 * wi + 2 * sp) * 8 + 2 * wj + kt) * 512);
-                    const uint32_t tileB = tileA + 8 * 512;                 // the strip below, same k-tile
-                    uint32_t fa[4], fb[4];
-                    ldsm_x4(fa, tileA + 16 * lane);
-                    ldsm_x4(fb, tileB + 16 * lane);
-                    mma_u8(c1[2 * sp], fa, bf1[kt]);
-                    mma_u8(c1[2 * sp + 1], fb, bf1[kt]);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {           // 16-column half h: matrices A(0,h) A(1,h) B(0,h) B(1,h)
-                        uint32_t r[4], f[4];
-                        ldsm_x4_trans(r, (mj < 2 ? tileA : tileB) + (uint32_t)(128 * ((mj & 1) + 2 * h) + 16 * mi));
-                        f[0] = __byte_perm(r[0], r[1], 0x6420);     // column 2g,   rows {2q, 2q+1, 8+2q, 9+2q} of strip a
-                        f[1] = __byte_perm(r[0], r[1], 0x7531);     // column 2g+1
-                        f[2] = __byte_perm(r[2], r[3], 0x6420);     // ... of strip b
-                        f[3] = __byte_perm(r[2], r[3], 0x7531);
-                        mma_u8(c2[kt][h], f, bf2[sp]);
+            if (tid == 0) {
+                int got = -1;
+                if (tk_valid) { got = sym_ticket_item(A, tk_r, tk_t); tk_valid = 0; }
+                const long long t_start = clock64();
+                unsigned long long skip = 0ull;     // chromosomes whose bit is still set but whose tickets just ran out
+                while (got < 0) {
+                    const unsigned long long m = ld_volatile_u64(A.avail) & ~skip;
+                    mask_seen = m;
+                    if (m != 0ull) {
+                        const int r = __ffsll((long long)m) - 1;
+                        got = sym_ticket_item(A, r, atomicAdd(A.tick + A.T.prio[r], 1));
+                        if (got < 0) skip |= 1ull << r;
+                        continue;
                     }
+                    skip = 0ull;
+                    if (ld_volatile_i32(A.n_active) <= 0 || ld_volatile_i32(A.abort_flag) != 0) break;
+                    if (clock64() - t_start > A.spin_limit) { atomicExch(A.abort_flag, 1); break; }
+                    __nanosleep(100);
+                }
+                sh_item[s] = got;
+                if (got >= 0) sym_issue_copy(A, got, smem_raw + s * BUF_BYTES, &bar[s]);
+            }
+            __syncthreads();
+            cur = sh_item[s];
+            if (cur < 0) break;
+        }
+        if (tid == 0) {
+            // the ticket requested during the previous block: its block goes into the earliest empty buffer
+            if (tk_valid) {
+                const int got = sym_ticket_item(A, tk_r, tk_t);
+                tk_valid = 0;
+                if (got >= 0) {
+                    const int x = sh_item[(s + 1) % NBUF] < 0 ? (s + 1) % NBUF : (s + 2) % NBUF;
+                    sh_item[x] = got;
+                    sym_issue_copy(A, got, smem_raw + x * BUF_BYTES, &bar[x]);
+                } else mask_seen &= ~(1ull << tk_r);       // its tickets ran out: try the next chromosome
+            }
+            // request the next one (looked at during the next block) and refresh the mask
+            if (mask_seen != 0ull && (sh_item[(s + 1) % NBUF] < 0 || sh_item[(s + 2) % NBUF] < 0)) {
+                tk_r = __ffsll((long long)mask_seen) - 1;
+                tk_t = atomicAdd(A.tick + A.T.prio[tk_r], 1);
+                tk_valid = 1;
+            }
+            mask_seen = ld_volatile_u64(A.avail);
+        }
+        const int4 d = __ldg(A.items + cur);
+        const int p = d.z, I = d.w & 0xffff, J = d.w >> 16;
+        const int nblk = A.T.nblk[p];
+        const int64_t npad = (int64_t)nblk * BLK;
+        const int dexp = __ldcg(A.dig_exp + p);                // used after the products: latency hidden
+        {                               // wait for the block (and its bias planes) to land
+            const uint32_t par = (phasebits >> s) & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&bar[s])), "r"(par) : "memory");
+            }
+            phasebits ^= 1u << s;
+        }
+        const unsigned char* bufp = smem_raw + s * BUF_BYTES;
+        const uint32_t base = smem_u32(bufp);
+        uint2 bf1[2], bf2[2];           // bias planes of this warp's columns (product 1) and rows (product 2)
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) bf1[kt] = *reinterpret_cast<const uint2*>(bufp + BLK_BYTES + (2 * wj + kt) * 256 + 8 * lane);
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) bf2[sp] = *reinterpret_cast<const uint2*>(bufp + BLK_BYTES + DIG_BYTES + (2 * wi + sp) * 256 + 8 * lane);
+        int c1[4][4], c2[2][2][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { c1[x][0] = 0; c1[x][1] = 0; c1[x][2] = 0; c1[x][3] = 0; }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { c2[kt][h][0] = 0; c2[kt][h][1] = 0; c2[kt][h][2] = 0; c2[kt][h][3] = 0; }
+        const int mj = lane >> 3, mi = lane & 7;         // ldmatrix.trans: lane supplies row mi of matrix mj
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint32_t tileA = base + (uint32_t)(((4 * wi + 2 * sp) * 8 + 2 * wj + kt) * 512);
+                const uint32_t tileB = tileA + 8 * 512;                 // the strip below, same k-tile
+                uint32_t fa[4], fb[4];
+                ldsm_x4(fa, tileA + 16 * lane);
+                ldsm_x4(fb, tileB + 16 * lane);
+                mma_u8(c1[2 * sp], fa, bf1[kt]);
+                mma_u8(c1[2 * sp + 1], fb, bf1[kt]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {           // 16-column half h: matrices A(0,h) A(1,h) B(0,h) B(1,h)
+                    uint32_t r[4], f[4];
+                    ldsm_x4_trans(r, (mj < 2 ? tileA : tileB) + (uint32_t)(128 * ((mj & 1) + 2 * h) + 16 * mi));
+                    f[0] = __byte_perm(r[0], r[1], 0x6420);     // column 2g,   rows {2q, 2q+1, 8+2q, 9+2q} of strip a
+                    f[1] = __byte_perm(r[0], r[1], 0x7531);     // column 2g+1
+                    f[2] = __byte_perm(r[2], r[3], 0x6420);     // ... of strip b
+                    f[3] = __byte_perm(r[2], r[3], 0x7531);
+                    mma_u8(c2[kt][h], f, bf2[sp]);
                 }
             }
-            // plane sums -> fp64, reduced over the 4 lanes of a group; cross-warp sums through shared memory
+        }
+        // plane sums -> fp64, reduced over the 4 lanes of a group; cross-warp sums through shared memory
+        const double scale = __longlong_as_double((long long)(1023 + dexp - 64) << 52);   // 2^(E - 64)
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                double va = ((double)c1[s][0] * w_even + (double)c1[s][1] * w_odd) * scale;
-                double vb = ((double)c1[s][2] * w_even + (double)c1[s][3] * w_odd) * scale;
+        for (int x = 0; x < 4; ++x) {
+            double va = ((double)c1[x][0] * w_even + (double)c1[x][1] * w_odd) * scale;
+            double vb = ((double)c1[x][2] * w_even + (double)c1[x][3] * w_odd) * scale;
+            va += __shfl_xor_sync(0xffffffffu, va, 1); va += __shfl_xor_sync(0xffffffffu, va, 2);
+            vb += __shfl_xor_sync(0xffffffffu, vb, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
+            if (q == 0) {
+                const int r0 = (4 * wi + x) * 16 + g;
+                red_r[wj * BLK + r0] = va;
+                red_r[wj * BLK + r0 + 8] = vb;
+            }
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double va = ((double)c2[kt][h][0] * w_even + (double)c2[kt][h][1] * w_odd) * scale;   // column 2g
+                double vb = ((double)c2[kt][h][2] * w_even + (double)c2[kt][h][3] * w_odd) * scale;   // column 2g+1
                 va += __shfl_xor_sync(0xffffffffu, va, 1); va += __shfl_xor_sync(0xffffffffu, va, 2);
                 vb += __shfl_xor_sync(0xffffffffu, vb, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
                 if (q == 0) {
-                    const int r0 = (4 * wi + s) * 16 + g;
-                    red_r[wj * BLK + r0] = va;
-                    red_r[wj * BLK + r0 + 8] = vb;
+                    const int cc = (2 * wj + kt) * 32 + 16 * h + 2 * g;
+                    red_c[wi * BLK + cc] = va;
+                    red_c[wi * BLK + cc + 1] = vb;
                 }
             }
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double va = ((double)c2[kt][h][0] * w_even + (double)c2[kt][h][1] * w_odd) * scale;   // column 2g
-                    double vb = ((double)c2[kt][h][2] * w_even + (double)c2[kt][h][3] * w_odd) * scale;   // column 2g+1
-                    va += __shfl_xor_sync(0xffffffffu, va, 1); va += __shfl_xor_sync(0xffffffffu, va, 2);
-                    vb += __shfl_xor_sync(0xffffffffu, vb, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
-                    if (q == 0) {
-                        const int cc = (2 * wj + kt) * 32 + 16 * h + 2 * g;
-                        red_c[wi * BLK + cc] = va;
-                        red_c[wi * BLK + cc + 1] = vb;
-                    }
-                }
-            __syncthreads();
-            double* part = A.part + A.T.part_off[p];
-            if (tid < 256) {
-                const double t = ((red_r[tid] + red_r[BLK + tid]) + red_r[2 * BLK + tid]) + red_r[3 * BLK + tid];
-                part[(int64_t)J * npad + I * BLK + tid] = t;                      // rows of block I, partial over the columns of block J
-            } else {
-                const int cdx = tid - 256;
-                const double t = ((red_c[cdx] + red_c[BLK + cdx]) + red_c[2 * BLK + cdx]) + red_c[3 * BLK + cdx];
-                part[(int64_t)(nblk + I) * npad + J * BLK + cdx] = t;             // columns of block J, partial over the rows of block I
-            }
-            __threadfence();
+        __syncthreads();                                                          // [B1]
+        double* part = A.part + A.T.part_off[p];
+        if (tid < 256) {
+            const double t = ((red_r[tid] + red_r[BLK + tid]) + red_r[2 * BLK + tid]) + red_r[3 * BLK + tid];
+            part[(int64_t)J * npad + I * BLK + tid] = t;                      // rows of block I, partial over the columns of block J
+        } else {
+            const int cdx = tid - 256;
+            const double t = ((red_c[cdx] + red_c[BLK + cdx]) + red_c[2 * BLK + cdx]) + red_c[3 * BLK + cdx];
+            part[(int64_t)(nblk + I) * npad + J * BLK + cdx] = t;             // columns of block J, partial over the rows of block I
         }
-        __syncthreads();
-        // thread 0: look at the completion counters the PREVIOUS item bumped (issued one item ago: no wait), then bump
-        // those of this item.  Block (I, J) feeds the bins of index I (row partials) and J (column partials); index b has
-        // all its nblk + 1 partial planes when its counter reaches nblk + 1.
+        __syncthreads();                                                          // [B2]
+        // thread 0: make the CTA's partial sums visible, look at the counters the PREVIOUS block bumped (no wait: they were
+        // bumped a block ago), bump this block's.  Block (I, J) feeds the bins of index I (row partials) and J (column
+        // partials); an index has all its nblk + 1 partial planes when its counter reaches nblk + 1.
         if (tid == 0) {
-            sh_flag[0] = 0;
-            if (pend_valid) {
-                const int need = A.T.nblk[pend_p] + 1;
-                const int fi = pend_I == pend_J ? (pend_oldI + 2 == need) : (pend_oldI + 1 == need);
-                const int fj = pend_I == pend_J ? 0 : (pend_oldJ + 1 == need);
-                if (fi || fj) { sh_flag[0] = 1; sh_flag[1] = pend_p; sh_flag[2] = pend_I; sh_flag[3] = pend_J; sh_flag[4] = fi; sh_flag[5] = fj; }
-                pend_valid = 0;
-            }
-            if (cur >= 0) {
-                const int4 d = __ldg(A.items + cur);
-                pend_p = d.z; pend_I = d.w & 0xffff; pend_J = d.w >> 16; pend_valid = 1;
-                int* bd = A.blkdone + A.T.blk_off[pend_p];
-                if (pend_I == pend_J) pend_oldI = atomicAdd(bd + pend_I, 2);
-                else { pend_oldI = atomicAdd(bd + pend_I, 1); pend_oldJ = atomicAdd(bd + pend_J, 1); }
-            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            resolve_pending();
+            pend_p = p; pend_I = I; pend_J = J; pend_valid = 1;
+            int* bd = A.blkdone + A.T.blk_off[p];
+            if (I == J) pend_oldI = atomicAdd(bd + I, 2);
+            else { pend_oldI = atomicAdd(bd + I, 1); pend_oldJ = atomicAdd(bd + J, 1); }
+            sh_item[s] = -1;
         }
-        __syncthreads();
-        if (sh_flag[0]) sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
-        if (cur >= 0) {                 // shift the queue
-            __syncthreads();
-            if (tid == 0) {
-                for (int x = 0; x + 1 < NBUF; ++x) sh_q[x] = sh_q[x + 1];
-                sh_q[NBUF - 1] = -1;
-            }
-            b0 = (b0 + 1) % NBUF;
-            __syncthreads();
-            continue;
-        }
-        // nothing in hand (and the pass above has resolved the last pending completion): wait for work, or for the end
-        if (warp == 0) {
-            int it = -1;
-            const long long t_start = clock64();
-            for (;;) {
-                it = sym_try_acquire(A, &hint);
-                if (it >= 0) break;
-                int act = 0;
-                if (lane == 0) {
-                    act = ld_volatile_i32(A.n_active);
-                    if (ld_volatile_i32(A.abort_flag) != 0) act = 0;
-                    else if (clock64() - t_start > A.spin_limit) { atomicExch(A.abort_flag, 1); act = 0; }
-                }
-                act = __shfl_sync(0xffffffffu, act, 0);
-                if (act <= 0) break;
-                __nanosleep(200);
-            }
-            if (lane == 0) {
-                sh_q[0] = it;
-                if (it >= 0) { __threadfence(); sym_issue_copy(A, it, smem_raw + b0 * BLK_BYTES, &bar[b0]); }
-            }
-        }
-        __syncthreads();
-        if (sh_q[0] < 0) break;
     }
 }
 
@@ -712,6 +707,7 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
                              const int64_t* bin_off, int32_t nprob, const int32_t* h_mat_n, const hc_ice_params* P,
                              double* bias, hc_ice_result* results, hc_ice_run_info* h_info, cudaStream_t s) {
     (void)mat_n;
+    if (nprob > 64) return 1;           // the availability mask is one 64-bit word
     for (int p = 0; p < nprob; ++p) if (h_mat_n[p] > MAX_BINS) return 1;
     int64_t nbins = 0;
     for (int p = 0; p < nprob; ++p) nbins += h_mat_n[p];
@@ -749,9 +745,9 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     if (h_info) { h_info->launches = 0; h_info->loop_ms = 0.f; h_info->packed = 3; h_info->pack_ms = 0.f; h_info->overflow_cells = 0; h_info->stream_full_ms = 0.f; h_info->stream_full_launches = 0; }
 
     Scratch scratch(s);
-    int32_t* d_i32 = nullptr;      // n | nblk | blk_off | item_first[nprob + 1] | prio
+    int32_t* d_i32 = nullptr;      // n | nblk | blk_off | item_first[nprob + 1] | prio | rank_of
     int64_t* d_i64 = nullptr;      // pad_off | part_off
-    HC_CUDA(scratch.alloc((void**)&d_i32, sizeof(int32_t) * (5 * (size_t)nprob + 1)));
+    HC_CUDA(scratch.alloc((void**)&d_i32, sizeof(int32_t) * (6 * (size_t)nprob + 1)));
     HC_CUDA(scratch.alloc((void**)&d_i64, sizeof(int64_t) * 2 * (size_t)nprob));
     std::vector<int32_t> h_i32;
     h_i32.insert(h_i32.end(), h_mat_n, h_mat_n + nprob);
@@ -759,6 +755,11 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     h_i32.insert(h_i32.end(), h_blkoff.begin(), h_blkoff.end());
     h_i32.insert(h_i32.end(), h_first.begin(), h_first.end());
     h_i32.insert(h_i32.end(), h_prio.begin(), h_prio.end());
+    {
+        std::vector<int32_t> h_rank(nprob);
+        for (int r = 0; r < nprob; ++r) h_rank[h_prio[r]] = r;
+        h_i32.insert(h_i32.end(), h_rank.begin(), h_rank.end());
+    }
     std::vector<int64_t> h_i64;
     h_i64.insert(h_i64.end(), h_pad.begin(), h_pad.end());
     h_i64.insert(h_i64.end(), h_part.begin(), h_part.end());
@@ -769,7 +770,7 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     HC_CUDA(cudaMemcpyAsync(d_items, h_items.data(), sizeof(int4) * (size_t)nitems, cudaMemcpyHostToDevice, s));
     SymTables T;
     T.n = d_i32; T.nblk = d_i32 + nprob; T.blk_off = d_i32 + 2 * nprob; T.item_first = d_i32 + 3 * nprob;
-    T.prio = d_i32 + 4 * nprob + 1;
+    T.prio = d_i32 + 4 * nprob + 1; T.rank_of = d_i32 + 5 * nprob + 1;
     T.pad_off = d_i64; T.part_off = d_i64 + nprob; T.bin_off = bin_off;
 
     cudaEvent_t evp0 = nullptr, evp1 = nullptr, ev0 = nullptr, ev1 = nullptr;
@@ -825,8 +826,11 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     h_book[4 * (size_t)nprob] = active;
     HC_CUDA(cudaMemcpyAsync(d_book, h_book.data(), sizeof(int32_t) * book_n, cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaMemcpyAsync(results, h_res.data(), sizeof(hc_ice_result) * (size_t)nprob, cudaMemcpyHostToDevice, s));
-    double* d_blk = nullptr;           // blk_sum[nblk_tot] | blk_cnt[nblk_tot] (int64)
-    HC_CUDA(scratch.alloc((void**)&d_blk, 16 * (size_t)nblk_tot));
+    double* d_blk = nullptr;           // blk_sum[nblk_tot] | blk_cnt[nblk_tot] (int64) | availability mask (uint64)
+    HC_CUDA(scratch.alloc((void**)&d_blk, 16 * (size_t)nblk_tot + 8));
+    unsigned long long h_avail = 0ull;              // every chromosome with blocks starts with its tickets open
+    for (int r = 0; r < nprob; ++r) if (h_first[h_prio[r] + 1] > h_first[h_prio[r]]) h_avail |= 1ull << r;
+    HC_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(d_blk) + 16 * (size_t)nblk_tot, &h_avail, 8, cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaStreamSynchronize(s));      // host staging vectors go out of use
 
     SymArgs A;
@@ -836,13 +840,14 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     A.n_active = d_book + 4 * nprob; A.abort_flag = d_book + 4 * nprob + 1; A.blkdone = d_book + 4 * nprob + 2;
     A.spin_limit = 4000000000ll;        // ~2 s at 1.9 GHz: no chromosome's update takes anywhere near that
     A.part = d_part; A.blk_sum = d_blk; A.blk_cnt = reinterpret_cast<long long*>(d_blk + nblk_tot);
+    A.avail = reinterpret_cast<unsigned long long*>(d_blk + 2 * (size_t)nblk_tot);
     A.ovf_ptr = d_ovf_ptr; A.ovf_col = d_ovf; A.ovf_val = d_ovf + novf;
     A.results = results; A.tol = P->tol; A.max_iters = P->max_iters;
     sym_init_kernel<<<nprob, SYM_THREADS, 0, s>>>(A, bias);
     HC_LAUNCH_CHECK();
     if (h_info && evp1) cudaEventRecord(evp1, s);
 
-    const size_t smem = 3 * (size_t)BLK_BYTES + 2 * 4 * BLK * sizeof(double);
+    const size_t smem = NBUF * (size_t)BUF_BYTES + 2 * 4 * BLK * sizeof(double);
     HC_CUDA(cudaFuncSetAttribute(sym_ice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(hc_num_sms(), nitems);
     if (h_info && ev0) cudaEventRecord(ev0, s);
