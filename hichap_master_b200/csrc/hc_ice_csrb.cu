@@ -41,7 +41,7 @@ constexpr int CB_BITS = 13;
 constexpr int CB = 1 << CB_BITS;            // bins per column block: 64 KB of fp64 bias
 constexpr int CNT_BITS = 32 - CB_BITS;      // 19
 constexpr long long CNT_MAX = (1ll << CNT_BITS) - 1;
-constexpr int ST_THREADS = 384;             // stream kernel: 3 CTAs x 384 threads x 64 KB per SM
+constexpr int ST_THREADS = 352;             // stream kernel: 3 CTAs x 352 threads x 64 KB per SM (<= 62 registers per thread)
 constexpr int ST_MINB = 3;
 constexpr int UPD_CLUSTER = 8;
 constexpr int UPD_THREADS = 1024;
@@ -213,46 +213,62 @@ struct CsrbArgs {
     const int64_t* bin_off; int nprob; const int32_t* done_at; const int32_t* n_done; int nonempty;
 };
 
+__device__ __forceinline__ void csrb_fma4(const int4& q, const double* __restrict__ sb, double& a0, double& a1) {
+    a0 = fma(i32_to_f64((int)((uint32_t)q.x >> CB_BITS)), sb[q.x & (CB - 1)], a0);
+    a1 = fma(i32_to_f64((int)((uint32_t)q.y >> CB_BITS)), sb[q.y & (CB - 1)], a1);
+    a0 = fma(i32_to_f64((int)((uint32_t)q.z >> CB_BITS)), sb[q.z & (CB - 1)], a0);
+    a1 = fma(i32_to_f64((int)((uint32_t)q.w >> CB_BITS)), sb[q.w & (CB - 1)], a1);
+}
+
+// One item: rows [r0, r1) of column block cb.  Groups of G lanes take rows round robin.  The segments are short (tens to
+// a few hundred entries), so a row is a chain of two dependent loads (segment bounds -> entries) with little work
+// behind it; the loop is therefore software-pipelined over rows: while row r is reduced, the first 128-bit vector of
+// the group's next row is in flight and the bounds of the one after that are being fetched (ncu on the unpipelined
+// version: long-scoreboard stalls dominate at 2.1 TB/s, profiles/r2c_ncu_csrb_stream_v1.json).
 template <int G>
 __device__ __forceinline__ void csrb_process_item(const CsrbArgs& A, const double* __restrict__ sb, int cb, int r0, int r1) {
     const int gl = threadIdx.x & (G - 1);
-    const int gid = threadIdx.x / G, ngroups = blockDim.x / G;
+    const int gid = threadIdx.x / G, ng = blockDim.x / G;
     // the groups of one warp run different numbers of rows: shuffle only among the lanes of the own group
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
     const int64_t* __restrict__ sp = A.seg_ptr + (long long)cb * A.nloc;
-    const int4* __restrict__ ent4 = reinterpret_cast<const int4*>(A.ent);
+    const long long base4 = __ldg(sp + r0) >> 2;                 // 128-bit vector index of the item's first entry
+    const int4* __restrict__ e4 = reinterpret_cast<const int4*>(A.ent) + base4;
     double* __restrict__ pout = A.part + (long long)cb * A.nloc;
-    for (int row = r0 + gid; row < r1; row += ngroups) {
-        if (A.nprob > 1) {
-            const int p = find_problem(A.bin_off, A.nprob, A.row0 + row);
-            if (A.done_at[p] != 0) continue;          // converged in an earlier iteration (group-uniform)
+    const int4 zero = make_int4(0, 0, 0, 0);
+    int row = r0 + gid;
+    int c0 = 0, c1 = 0, n0 = 0, n1 = 0, m0 = 0, m1 = 0;          // bounds (vectors, relative to base4) of this row, the next, the one after
+    if (row < r1) { c0 = (int)((__ldg(sp + row) >> 2) - base4); c1 = (int)((__ldg(sp + row + 1) >> 2) - base4); }
+    if (row + ng < r1) { n0 = (int)((__ldg(sp + row + ng) >> 2) - base4); n1 = (int)((__ldg(sp + row + ng + 1) >> 2) - base4); }
+    int4 qc = (row < r1 && c0 + gl < c1) ? ld_stream_v4(reinterpret_cast<const int32_t*>(e4 + c0 + gl)) : zero;
+    for (; row < r1; row += ng) {
+        if (row + 2 * ng < r1) {
+            m0 = (int)((__ldg(sp + row + 2 * ng) >> 2) - base4);
+            m1 = (int)((__ldg(sp + row + 2 * ng + 1) >> 2) - base4);
         }
-        const long long v0 = sp[row] >> 2, v1 = sp[row + 1] >> 2;
-        double a0 = 0.0, a1 = 0.0;
-        long long v = v0 + gl;
-        for (; v + G < v1; v += 2 * G) {           // two 128-bit loads in flight per lane
-            const int4 q = ld_stream_v4(reinterpret_cast<const int32_t*>(ent4 + v));
-            const int4 u = ld_stream_v4(reinterpret_cast<const int32_t*>(ent4 + v + G));
-            a0 = fma(i32_to_f64((int)((uint32_t)q.x >> CB_BITS)), sb[q.x & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)q.y >> CB_BITS)), sb[q.y & (CB - 1)], a1);
-            a0 = fma(i32_to_f64((int)((uint32_t)q.z >> CB_BITS)), sb[q.z & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)q.w >> CB_BITS)), sb[q.w & (CB - 1)], a1);
-            a0 = fma(i32_to_f64((int)((uint32_t)u.x >> CB_BITS)), sb[u.x & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)u.y >> CB_BITS)), sb[u.y & (CB - 1)], a1);
-            a0 = fma(i32_to_f64((int)((uint32_t)u.z >> CB_BITS)), sb[u.z & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)u.w >> CB_BITS)), sb[u.w & (CB - 1)], a1);
-        }
-        if (v < v1) {
-            const int4 q = ld_stream_v4(reinterpret_cast<const int32_t*>(ent4 + v));
-            a0 = fma(i32_to_f64((int)((uint32_t)q.x >> CB_BITS)), sb[q.x & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)q.y >> CB_BITS)), sb[q.y & (CB - 1)], a1);
-            a0 = fma(i32_to_f64((int)((uint32_t)q.z >> CB_BITS)), sb[q.z & (CB - 1)], a0);
-            a1 = fma(i32_to_f64((int)((uint32_t)q.w >> CB_BITS)), sb[q.w & (CB - 1)], a1);
-        }
-        double acc = a0 + a1;
+        const int4 qn = (row + ng < r1 && n0 + gl < n1) ? ld_stream_v4(reinterpret_cast<const int32_t*>(e4 + n0 + gl)) : zero;
+        bool live = true;
+        if (A.nprob > 1) live = A.done_at[find_problem(A.bin_off, A.nprob, A.row0 + row)] == 0;   // group-uniform
+        if (live) {
+            double a0 = 0.0, a1 = 0.0;
+            csrb_fma4(qc, sb, a0, a1);                    // an absent vector is all zero: count 0 times sb[0]
+            int v = c0 + gl + G;
+            for (; v + G < c1; v += 2 * G) {              // two 128-bit loads in flight per lane
+                const int4 q = ld_stream_v4(reinterpret_cast<const int32_t*>(e4 + v));
+                const int4 u = ld_stream_v4(reinterpret_cast<const int32_t*>(e4 + v + G));
+                csrb_fma4(q, sb, a0, a1);
+                csrb_fma4(u, sb, a0, a1);
+            }
+            if (v < c1) {
+                const int4 q = ld_stream_v4(reinterpret_cast<const int32_t*>(e4 + v));
+                csrb_fma4(q, sb, a0, a1);
+            }
+            double acc = a0 + a1;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-        if (gl == 0) pout[row] = acc;
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+            if (gl == 0) pout[row] = acc;
+        }
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1; qc = qn;
     }
 }
 
