@@ -195,6 +195,8 @@ struct SymArgs {
     unsigned long long* avail;                  // bit r: the chromosome of priority rank r has tickets left this iteration
     int32_t* abort_flag;                        // set by a CTA that waited implausibly long for work (dataflow bug guard)
     long long spin_limit;                       // clock64 ticks a CTA may wait for work before it raises abort_flag
+    long long* stats;                           // HC_SYM_STATS=1: per CTA {blocks, cycles waiting for work, cycles in phases, cycles
+                                                // waiting for a bulk copy, total cycles, waits for work, failed tickets, phases run}
     double* blk_sum; long long* blk_cnt;        // per block: sum / count of the non-zero marginals (phase A -> phase B)
     const int64_t* ovf_ptr; const int32_t* ovf_col; const int32_t* ovf_val;
     hc_ice_result* results; double tol; int max_iters;
@@ -311,15 +313,26 @@ __device__ void sym_phase_a(const SymArgs& A, int p, int b, double* red, long lo
     const double* part = A.part + A.T.part_off[p];
     const int tid = threadIdx.x, idx = b * BLK + (tid & 255);
     double t = 0.0;
+    // the partial planes are summed four at a time (independent loads in flight), in a fixed order
+    auto plane_sum = [&](int first, int last) {       // planes first .. last-1 at idx
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int k = first;
+        for (; k + 3 < last; k += 4) {
+            t0 += __ldcg(part + (int64_t)k * npad + idx); t1 += __ldcg(part + (int64_t)(k + 1) * npad + idx);
+            t2 += __ldcg(part + (int64_t)(k + 2) * npad + idx); t3 += __ldcg(part + (int64_t)(k + 3) * npad + idx);
+        }
+        for (; k < last; ++k) t0 += __ldcg(part + (int64_t)k * npad + idx);
+        return (t0 + t1) + (t2 + t3);
+    };
     if (tid < 256) {                                  // row partials of blocks (b, J), J = b .. nblk-1
-        for (int J = b; J < nblk; ++J) t += __ldcg(part + (int64_t)J * npad + idx);
+        t = plane_sum(b, nblk);
         const int64_t g = A.T.bin_off[p] + idx;       // + the row's overflow cells
         if (idx < n) {
             const double* bw = A.bias + lo;
             for (int64_t e = A.ovf_ptr[g]; e < A.ovf_ptr[g + 1]; ++e) t = fma((double)A.ovf_val[e], __ldcg(bw + A.ovf_col[e]), t);
         }
     } else {                                          // column partials of blocks (I, b), I = 0 .. b
-        for (int I = 0; I <= b; ++I) t += __ldcg(part + (int64_t)(nblk + I) * npad + idx);
+        t = plane_sum(nblk, nblk + b + 1);
         xch[tid & 255] = t;
     }
     __syncthreads();
@@ -458,6 +471,8 @@ sym_ice_kernel(SymArgs A) {
     int tk_valid = 0, tk_r = 0, tk_t = 0;
     unsigned long long mask_seen = 0ull;
     int pend_valid = 0, pend_p = 0, pend_I = 0, pend_J = 0, pend_oldI = 0, pend_oldJ = 0;
+    long long st_items = 0, st_wait = 0, st_phase = 0, st_copy = 0, st_nwait = 0, st_fail = 0, st_nphase = 0;
+    const long long st_t0 = clock64();
     if (tid == 0) {
         for (int x = 0; x < NBUF; ++x) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar[x])), "r"(1) : "memory");
@@ -479,7 +494,11 @@ sym_ice_kernel(SymArgs A) {
     for (int it = 0;; ++it) {
         const int s = it % NBUF;
         __syncthreads();                                                          // [B0]
-        if (sh_flag[0]) sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
+        if (sh_flag[0]) {
+            const long long t = clock64();
+            sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
+            st_phase += clock64() - t; ++st_nphase;
+        }
         int cur = sh_item[s];
         if (cur < 0) {
             // Nothing in hand (then no buffer holds a block: they fill in order).  Settle what is outstanding, then wait for
@@ -488,7 +507,9 @@ sym_ice_kernel(SymArgs A) {
             if (tid == 0) resolve_pending();
             __syncthreads();
             if (sh_flag[0]) {
+                const long long t = clock64();
                 sym_phases(A, sh_flag[1], sh_flag[2], sh_flag[3], sh_flag[4], sh_flag[5], red, redll, red_r, &sh_flag[6]);
+                st_phase += clock64() - t; ++st_nphase;
                 if (tid == 0) sh_flag[0] = 0;
             }
             if (tid == 0) {
@@ -502,7 +523,7 @@ sym_ice_kernel(SymArgs A) {
                     if (m != 0ull) {
                         const int r = __ffsll((long long)m) - 1;
                         got = sym_ticket_item(A, r, atomicAdd(A.tick + A.T.prio[r], 1));
-                        if (got < 0) skip |= 1ull << r;
+                        if (got < 0) { skip |= 1ull << r; ++st_fail; }
                         continue;
                     }
                     skip = 0ull;
@@ -512,6 +533,7 @@ sym_ice_kernel(SymArgs A) {
                 }
                 sh_item[s] = got;
                 if (got >= 0) sym_issue_copy(A, got, smem_raw + s * BUF_BYTES, &bar[s]);
+                st_wait += clock64() - t_start; ++st_nwait;
             }
             __syncthreads();
             cur = sh_item[s];
@@ -526,7 +548,7 @@ sym_ice_kernel(SymArgs A) {
                     const int x = sh_item[(s + 1) % NBUF] < 0 ? (s + 1) % NBUF : (s + 2) % NBUF;
                     sh_item[x] = got;
                     sym_issue_copy(A, got, smem_raw + x * BUF_BYTES, &bar[x]);
-                } else mask_seen &= ~(1ull << tk_r);       // its tickets ran out: try the next chromosome
+                } else { mask_seen &= ~(1ull << tk_r); ++st_fail; }      // its tickets ran out: try the next chromosome
             }
             // request the next one (looked at during the next block) and refresh the mask
             if (mask_seen != 0ull && (sh_item[(s + 1) % NBUF] < 0 || sh_item[(s + 2) % NBUF] < 0)) {
@@ -541,6 +563,8 @@ sym_ice_kernel(SymArgs A) {
         const int nblk = A.T.nblk[p];
         const int64_t npad = (int64_t)nblk * BLK;
         const int dexp = __ldcg(A.dig_exp + p);                // used after the products: latency hidden
+        ++st_items;
+        const long long st_c0 = clock64();
         {                               // wait for the block (and its bias planes) to land
             const uint32_t par = (phasebits >> s) & 1u;
             uint32_t done = 0;
@@ -550,6 +574,7 @@ sym_ice_kernel(SymArgs A) {
             }
             phasebits ^= 1u << s;
         }
+        st_copy += clock64() - st_c0;
         const unsigned char* bufp = smem_raw + s * BUF_BYTES;
         const uint32_t base = smem_u32(bufp);
         uint2 bf1[2], bf2[2];           // bias planes of this warp's columns (product 1) and rows (product 2)
@@ -639,6 +664,10 @@ sym_ice_kernel(SymArgs A) {
             else { pend_oldI = atomicAdd(bd + I, 1); pend_oldJ = atomicAdd(bd + J, 1); }
             sh_item[s] = -1;
         }
+    }
+    if (tid == 0 && A.stats != nullptr) {
+        long long* o = A.stats + 8 * (long long)blockIdx.x;
+        o[0] = st_items; o[1] = st_wait; o[2] = st_phase; o[3] = st_copy; o[4] = clock64() - st_t0; o[5] = st_nwait; o[6] = st_fail; o[7] = st_nphase;
     }
 }
 
@@ -839,6 +868,13 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     A.tick = d_book; A.adone = d_book + nprob; A.iters = d_book + 2 * nprob; A.dig_exp = d_book + 3 * nprob;
     A.n_active = d_book + 4 * nprob; A.abort_flag = d_book + 4 * nprob + 1; A.blkdone = d_book + 4 * nprob + 2;
     A.spin_limit = 4000000000ll;        // ~2 s at 1.9 GHz: no chromosome's update takes anywhere near that
+    A.stats = nullptr;
+    const bool want_stats = getenv("HC_SYM_STATS") != nullptr && atoi(getenv("HC_SYM_STATS")) != 0;
+    const int grid = std::min(hc_num_sms(), nitems);
+    if (want_stats) {
+        HC_CUDA(scratch.alloc((void**)&A.stats, sizeof(long long) * 8 * (size_t)grid));
+        HC_CUDA(cudaMemsetAsync(A.stats, 0, sizeof(long long) * 8 * (size_t)grid, s));
+    }
     A.part = d_part; A.blk_sum = d_blk; A.blk_cnt = reinterpret_cast<long long*>(d_blk + nblk_tot);
     A.avail = reinterpret_cast<unsigned long long*>(d_blk + 2 * (size_t)nblk_tot);
     A.ovf_ptr = d_ovf_ptr; A.ovf_col = d_ovf; A.ovf_val = d_ovf + novf;
@@ -849,7 +885,6 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
 
     const size_t smem = NBUF * (size_t)BUF_BYTES + 2 * 4 * BLK * sizeof(double);
     HC_CUDA(cudaFuncSetAttribute(sym_ice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(hc_num_sms(), nitems);
     if (h_info && ev0) cudaEventRecord(ev0, s);
     sym_ice_kernel<<<grid, SYM_THREADS, smem, s>>>(A);
     HC_LAUNCH_CHECK();
@@ -860,6 +895,17 @@ int hc_ice_dense_balance_sym(const int32_t* mats, const int64_t* mat_off, const 
     const cudaError_t e = hc_read_small(&h_abort, A.abort_flag, sizeof(int32_t), s);
     if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance (symmetric): %s", cudaGetErrorString(e)); return HC_ERR_CUDA; }
     if (h_abort) { hc_set_error("hc_ice_dense_balance (symmetric): the dataflow kernel stalled (a CTA waited > 2 s for work)"); return HC_ERR_CUDA; }
+    if (want_stats) {
+        std::vector<long long> h_st(8 * (size_t)grid);
+        HC_CUDA(cudaMemcpyAsync(h_st.data(), A.stats, sizeof(long long) * h_st.size(), cudaMemcpyDeviceToHost, s));
+        HC_CUDA(cudaStreamSynchronize(s));
+        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) sum[k] += (double)h_st[8 * (size_t)b + k];
+        fprintf(stderr, "[sym_ice_kernel] %d CTAs; per CTA: %.0f blocks, %.0f waits for work, %.0f failed tickets, %.0f phase runs; "
+                "cycles: total %.0f = waiting for work %.1f %% + phases %.1f %% + waiting for a bulk copy %.1f %% + rest %.1f %%\n",
+                grid, sum[0] / grid, sum[5] / grid, sum[6] / grid, sum[7] / grid, sum[4] / grid, 100 * sum[1] / sum[4], 100 * sum[2] / sum[4],
+                100 * sum[3] / sum[4], 100 * (sum[4] - sum[1] - sum[2] - sum[3]) / sum[4]);
+    }
     if (h_info) {
         h_info->launches = 5 + (novf > 0 ? 1 : 0);
         h_info->packed = 3;
