@@ -468,7 +468,7 @@ sym_ice_kernel(SymArgs A) {
     const double w_odd = __longlong_as_double((long long)(1023 + 8 * (6 - 2 * q)) << 52);
     uint32_t phasebits = 0u;            // expected parity of each buffer's mbarrier
     // thread 0 only: the outstanding ticket, the last availability mask seen, the completion counters not yet looked at
-    int tk_valid = 0, tk_r = 0, tk_t = 0;
+    int tk_n = 0, tk_r = 0, tk_t0 = 0, tk_t1 = 0;           // up to two tickets (of the same chromosome) in flight
     unsigned long long mask_seen = 0ull;
     int pend_valid = 0, pend_p = 0, pend_I = 0, pend_J = 0, pend_oldI = 0, pend_oldJ = 0;
     long long st_items = 0, st_wait = 0, st_phase = 0, st_copy = 0, st_nwait = 0, st_fail = 0, st_nphase = 0;
@@ -514,7 +514,6 @@ sym_ice_kernel(SymArgs A) {
             }
             if (tid == 0) {
                 int got = -1;
-                if (tk_valid) { got = sym_ticket_item(A, tk_r, tk_t); tk_valid = 0; }
                 const long long t_start = clock64();
                 unsigned long long skip = 0ull;     // chromosomes whose bit is still set but whose tickets just ran out
                 while (got < 0) {
@@ -540,21 +539,14 @@ sym_ice_kernel(SymArgs A) {
             if (cur < 0) break;
         }
         if (tid == 0) {
-            // the ticket requested during the previous block: its block goes into the earliest empty buffer
-            if (tk_valid) {
-                const int got = sym_ticket_item(A, tk_r, tk_t);
-                tk_valid = 0;
-                if (got >= 0) {
-                    const int x = sh_item[(s + 1) % NBUF] < 0 ? (s + 1) % NBUF : (s + 2) % NBUF;
-                    sh_item[x] = got;
-                    sym_issue_copy(A, got, smem_raw + x * BUF_BYTES, &bar[x]);
-                } else { mask_seen &= ~(1ull << tk_r); ++st_fail; }      // its tickets ran out: try the next chromosome
-            }
-            // request the next one (looked at during the next block) and refresh the mask
-            if (mask_seen != 0ull && (sh_item[(s + 1) % NBUF] < 0 || sh_item[(s + 2) % NBUF] < 0)) {
+            // request a ticket for every buffer that will be empty after this block (looked at after the block) and refresh
+            // the mask
+            const int empty = min(2, 1 + (sh_item[(s + 1) % NBUF] < 0) + (sh_item[(s + 2) % NBUF] < 0));
+            if (mask_seen != 0ull) {
                 tk_r = __ffsll((long long)mask_seen) - 1;
-                tk_t = atomicAdd(A.tick + A.T.prio[tk_r], 1);
-                tk_valid = 1;
+                if (empty >= 1) tk_t0 = atomicAdd(A.tick + A.T.prio[tk_r], 1);
+                if (empty >= 2) tk_t1 = atomicAdd(A.tick + A.T.prio[tk_r], 1);
+                tk_n = empty;
             }
             mask_seen = ld_volatile_u64(A.avail);
         }
@@ -663,6 +655,20 @@ sym_ice_kernel(SymArgs A) {
             if (I == J) pend_oldI = atomicAdd(bd + I, 2);
             else { pend_oldI = atomicAdd(bd + I, 1); pend_oldJ = atomicAdd(bd + J, 1); }
             sh_item[s] = -1;
+            // the tickets requested at the top of this block: their blocks go into the earliest empty buffers in processing
+            // order (s+1, s+2, then s again) and their bulk copies start now, one to three blocks before they are needed
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k < tk_n) {
+                    const int got = sym_ticket_item(A, tk_r, k == 0 ? tk_t0 : tk_t1);
+                    if (got >= 0) {
+                        const int x = sh_item[(s + 1) % NBUF] < 0 ? (s + 1) % NBUF : (sh_item[(s + 2) % NBUF] < 0 ? (s + 2) % NBUF : s);
+                        sh_item[x] = got;
+                        sym_issue_copy(A, got, smem_raw + x * BUF_BYTES, &bar[x]);
+                    } else { mask_seen &= ~(1ull << tk_r); ++st_fail; }      // its tickets ran out: try the next chromosome
+                }
+            }
+            tk_n = 0;
         }
     }
     if (tid == 0 && A.stats != nullptr) {
