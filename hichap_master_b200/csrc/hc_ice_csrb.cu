@@ -179,7 +179,7 @@ __global__ void csrb_block_totals_kernel(const int64_t* __restrict__ seg_ptr, lo
 // desc = {cb, first row, end row, log2 of the lane-group size}
 __global__ void __launch_bounds__(256)
 csrb_items_kernel(const int64_t* __restrict__ seg_ptr, long long nloc, int nb, const int32_t* __restrict__ item_first,
-                  int nitems, long long target, int4* __restrict__ desc) {
+                  int nitems, long long target, int4 gthr, int4* __restrict__ desc) {
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= nitems) return;
     int lo = 0, hi = nb - 1;
@@ -197,7 +197,8 @@ csrb_items_kernel(const int64_t* __restrict__ seg_ptr, long long nloc, int nb, c
     const long long entries = sp[r1] - sp[r0];          // sp[nloc] is the next block's first segment (or the total)
     const long long rows = r1 > r0 ? r1 - r0 : 1;
     const long long avg = entries / rows;
-    const int glog = avg >= 192 ? 5 : (avg >= 20 ? 3 : 1);
+    // lanes per segment: fewer lanes per segment = more segments (independent load chains) in flight per warp
+    const int glog = avg >= gthr.w ? 5 : (avg >= gthr.z ? 4 : (avg >= gthr.y ? 3 : (avg >= gthr.x ? 2 : 1)));
     desc[it] = make_int4(cb, (int)r0, (int)r1, glog);
 }
 
@@ -310,7 +311,9 @@ csrb_stream_kernel(CsrbArgs A) {
             staged = d.x;
         }
         if (d.w == 5) csrb_process_item<32>(A, sb, d.x, d.y, d.z);
+        else if (d.w == 4) csrb_process_item<16>(A, sb, d.x, d.y, d.z);
         else if (d.w == 3) csrb_process_item<8>(A, sb, d.x, d.y, d.z);
+        else if (d.w == 2) csrb_process_item<4>(A, sb, d.x, d.y, d.z);
         else csrb_process_item<2>(A, sb, d.x, d.y, d.z);
     }
 }
@@ -529,8 +532,14 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
     HC_CUDA(scratch.alloc((void**)&d_items, sizeof(int4) * (size_t)std::max(nitems, 1)));
     HC_CUDA(scratch.alloc((void**)&d_first, sizeof(int32_t) * (nb + 1)));
     HC_CUDA(cudaMemcpyAsync(d_first, h_first.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, s));
+    // average segment length from which a segment gets 4 / 8 / 16 / 32 lanes (HC_CSRB_GTHR="a,b,c,d" overrides)
+    int4 gthr = make_int4(12, 48, 256, 1024);
+    if (const char* e = getenv("HC_CSRB_GTHR")) {
+        int a = 0, b = 0, c = 0, d = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) gthr = make_int4(a, b, c, d);
+    }
     if (nitems > 0) {
-        csrb_items_kernel<<<(nitems + 255) / 256, 256, 0, s>>>(d_seg, nloc, nb, d_first, nitems, target, d_items);
+        csrb_items_kernel<<<(nitems + 255) / 256, 256, 0, s>>>(d_seg, nloc, nb, d_first, nitems, target, gthr, d_items);
         HC_LAUNCH_CHECK();
     }
     HC_CUDA(cudaStreamSynchronize(s));             // h_first goes out of use
