@@ -533,7 +533,7 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
     HC_CUDA(scratch.alloc((void**)&d_first, sizeof(int32_t) * (nb + 1)));
     HC_CUDA(cudaMemcpyAsync(d_first, h_first.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, s));
     // average segment length from which a segment gets 4 / 8 / 16 / 32 lanes (HC_CSRB_GTHR="a,b,c,d" overrides)
-    int4 gthr = make_int4(12, 48, 256, 1024);
+    int4 gthr = make_int4(8, 32, 128, 512);      // measured on C4 (profiles/README.md): flat between these and (20, 20, 192, 192)
     if (const char* e = getenv("HC_CSRB_GTHR")) {
         int a = 0, b = 0, c = 0, d = 0;
         if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) gthr = make_int4(a, b, c, d);

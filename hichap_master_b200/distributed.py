@@ -52,16 +52,22 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     skeys, _, n_valid = kernels.pairs_to_sorted_keys(pairs, res, start, chrom_bins, nbins, cis_only)
     m = int(n_valid.item())
     skeys = skeys[:m]
-    # per-row key counts (keys are sorted by row): the only torch math on this path is this
-    # histogram used to agree on the row boundaries
-    rows = (skeys >> col_bits)
-    hist = torch.bincount(rows, minlength=nbins).to(torch.int64)
+    # per-row key counts: the keys are sorted, so the first key of every row is a binary search away (nbins searches
+    # instead of a histogram over up to 2 G keys).  This bookkeeping, used to agree on the row boundaries, is the only
+    # torch math on the path.
+    edges = torch.arange(nbins + 1, dtype=torch.int64, device=dev) << col_bits
+    pos = torch.searchsorted(skeys, edges)                       # first key with row >= r
+    hist = pos[1:] - pos[:-1]
     # cut on DISTINCT keys per row (what a rank will store after reduce-by-key), not on pairs: the many duplicate
     # pairs next to the diagonal would otherwise skew the cuts (a key held by several ranks is counted once per rank)
     if m > 1:
-        first = torch.ones(m, dtype=torch.bool, device=dev)
-        first[1:] = skeys[1:] != skeys[:-1]
-        total = torch.bincount(rows[first], minlength=nbins).to(torch.int64)
+        first = torch.ones(m, dtype=torch.int32, device=dev)
+        first[1:] = (skeys[1:] != skeys[:-1]).to(torch.int32)
+        cd = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(first, 0, out=cd[1:])
+        del first
+        total = cd[pos[1:]] - cd[pos[:-1]]
+        del cd
     else:
         total = hist.clone()
     dist.all_reduce(total)

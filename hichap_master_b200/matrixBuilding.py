@@ -601,6 +601,13 @@ def ice_balance_sparse(csr, Bins, cis_only=False, ignore_diags=1, mad_max=5, min
     return bias.cpu().numpy(), stats
 
 
-# drivers (replicate loop, merge, stores): same names as the reference, defined in construction.py
-from .construction import (Check_Bed, HaplotypeMatrixBuilding, HaplotypeMatrixConstruction, Merge_beds,  # noqa: E402,F401
-                           TraditionalMatrixConstruction)
+# drivers (replicate loop, merge, stores): same names as the reference, defined in construction.py (which imports this
+# module): resolved on first use so that either module can be imported first
+_DRIVERS = ("Check_Bed", "HaplotypeMatrixBuilding", "HaplotypeMatrixConstruction", "Merge_beds", "TraditionalMatrixConstruction")
+
+
+def __getattr__(name):
+    if name in _DRIVERS:
+        from . import construction
+        return getattr(construction, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
