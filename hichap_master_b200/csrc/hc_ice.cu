@@ -1252,32 +1252,77 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
     // HC_ICE_TIME_KERNEL=1 (set by bench.py): the first stream-kernel launch of every graph replay is bracketed by a pair
     // of events, so that its duration can be read back separately from the update kernel and the launch gaps (external
     // event-record nodes inside the graph; bracketing all 8 launches of a replay cost ~11 us per iteration)
-    struct EventList {
-        std::vector<cudaEvent_t> ev;
-        ~EventList() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
-    } sev;
-    if (h_info != nullptr && getenv("HC_ICE_TIME_KERNEL") != nullptr && atoi(getenv("HC_ICE_TIME_KERNEL")) != 0) {
-        sev.ev.assign(2, nullptr);
-        for (auto& e : sev.ev) if (cudaEventCreate(&e) != cudaSuccess) { e = nullptr; }
-        for (auto& e : sev.ev) if (e == nullptr) { for (auto& x : sev.ev) { if (x) cudaEventDestroy(x); x = nullptr; } sev.ev.clear(); break; }
+    // The captured graph is kept between calls (per host thread): the next call with the same launch shape only
+    // rewrites the kernel parameters of its nodes (cudaGraphExecKernelNodeSetParams) instead of capturing and
+    // instantiating again -- ~0.4 ms of host time per call on C2.
+    // HC_ICE_TIME_KERNEL=1 (set by bench.py): the first stream-kernel launch of every graph replay is bracketed by a pair
+    // of events, so that its duration can be read back separately from the update kernel and the launch gaps (external
+    // event-record nodes inside the graph; bracketing all 8 launches of a replay cost ~11 us per iteration)
+    struct GraphCache {
+        cudaGraphExec_t exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        std::vector<cudaGraphNode_t> knodes;
+        void* fn = nullptr;
+        int grid = 0, poll = 0, nprob = 0, cluster = 0, timed = 0, dev = -1;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        void drop() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            exec = nullptr; graph = nullptr; knodes.clear();
+        }
+    };
+    static thread_local GraphCache gc;
+    const bool timed = h_info != nullptr && getenv("HC_ICE_TIME_KERNEL") != nullptr && atoi(getenv("HC_ICE_TIME_KERNEL")) != 0;
+    struct { std::vector<cudaEvent_t> ev; } sev;
+    if (timed) {
+        for (auto& e : gc.ev) if (e == nullptr && cudaEventCreate(&e) != cudaSuccess) { e = nullptr; (void)cudaGetLastError(); }
+        if (gc.ev[0] && gc.ev[1]) sev.ev.assign(gc.ev, gc.ev + 2);
     }
     double stream_ms_sum = 0.0;
     int stream_ms_n = 0;
     if (use_graph) {
-        cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-        if (e == cudaSuccess) {
-            for (int i = 0; i < poll; ++i) {
-                if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[0], s, cudaEventRecordExternal);
-                V.fn<<<grid, 256, smem, s>>>(A);
-                if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[1], s, cudaEventRecordExternal);
-                launch_update();
+        const bool hit = gc.exec != nullptr && gc.fn == (void*)V.fn && gc.grid == grid && gc.poll == poll && gc.nprob == nprob &&
+                         gc.cluster == (int)cluster_update && gc.timed == (int)!sev.ev.empty() && gc.dev == dev;
+        cudaError_t e = cudaSuccess;
+        if (hit) {
+            for (cudaGraphNode_t node : gc.knodes) {
+                cudaKernelNodeParams kp;
+                e = cudaGraphKernelNodeGetParams(node, &kp);
+                void* args[1] = {&A};
+                kp.kernelParams = args;
+                if (e == cudaSuccess) e = cudaGraphExecKernelNodeSetParams(gc.exec, node, &kp);
+                if (e != cudaSuccess) break;
             }
-            e = cudaStreamEndCapture(s, &graph);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); gc.drop(); }
         }
-        if (e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
-        if (graph) cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { gexec = nullptr; (void)cudaGetLastError(); }   // plain launches below
+        if (gc.exec == nullptr) {
+            e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                for (int i = 0; i < poll; ++i) {
+                    if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[0], s, cudaEventRecordExternal);
+                    V.fn<<<grid, 256, smem, s>>>(A);
+                    if (i == 0 && !sev.ev.empty()) cudaEventRecordWithFlags(sev.ev[1], s, cudaEventRecordExternal);
+                    launch_update();
+                }
+                e = cudaStreamEndCapture(s, &gc.graph);
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&gc.exec, gc.graph, 0);
+            if (e == cudaSuccess) {
+                size_t nn = 0;
+                e = cudaGraphGetNodes(gc.graph, nullptr, &nn);
+                std::vector<cudaGraphNode_t> nodes(nn);
+                if (e == cudaSuccess && nn) e = cudaGraphGetNodes(gc.graph, nodes.data(), &nn);
+                for (size_t k = 0; e == cudaSuccess && k < nn; ++k) {
+                    cudaGraphNodeType t;
+                    e = cudaGraphNodeGetType(nodes[k], &t);
+                    if (e == cudaSuccess && t == cudaGraphNodeTypeKernel) gc.knodes.push_back(nodes[k]);
+                }
+            }
+            if (e != cudaSuccess) { gc.drop(); (void)cudaGetLastError(); }   // plain launches below
+            else { gc.fn = (void*)V.fn; gc.grid = grid; gc.poll = poll; gc.nprob = nprob; gc.cluster = (int)cluster_update;
+                   gc.timed = (int)!sev.ev.empty(); gc.dev = dev; }
+        }
+        gexec = gc.exec;
     }
     EventPair evl;                              // device time of the iteration loop, for the roofline
     cudaEvent_t& ev0 = evl.a;
@@ -1311,7 +1356,6 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
         if (e != cudaSuccess) { hc_set_error("hc_ice_dense_balance: %s", cudaGetErrorString(e)); rc = HC_ERR_CUDA; break; }
     }
     if (h_info && ev0) cudaEventRecord(ev1, s);
-    if (gexec) cudaGraphExecDestroy(gexec);
     if (rc == HC_OK) {
         const int64_t blocks = (nbins + 255) / 256;
         ice_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin_off, d_pad, nprob, results, P->rescale_marginals, biasp, bias);
