@@ -1294,7 +1294,7 @@ extern "C" int hc_ice_dense_balance(const int32_t* mats, const int64_t* mat_off,
                 if (e != cudaSuccess) break;
             }
             if (e != cudaSuccess) { (void)cudaGetLastError(); gc.drop(); }
-        }
+        } else gc.drop();               // another launch shape: capture again
         if (gc.exec == nullptr) {
             e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
             if (e == cudaSuccess) {

@@ -325,7 +325,7 @@ csrb_stream_kernel(CsrbArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------
-// TMA-fed variant (default): the entries themselves are staged in shared memory by bulk copies
+// TMA-fed variant (opt-in, HC_CSRB_TMA=1): the entries themselves are staged in shared memory by bulk copies
 // ---------------------------------------------------------------------------------------
 // ncu on the kernel above (profiles/r2e_ncu_csrb_stream_v2.json): long-scoreboard stalls on the entry / bounds loads
 // dominate at 50 % issue activity and 3.0 TB/s.  An item's entries are one contiguous byte range, so here the producer
@@ -333,6 +333,10 @@ csrb_stream_kernel(CsrbArgs A) {
 // only ever read shared memory: LDS.128 for the entries, LDS.64 for the bias gathers.  Items are capped at TMA_ROWS rows
 // and assigned to the CTAs statically (item i -> CTA i mod grid; they are of near-equal size), so the loop has no queue
 // and no CTA-wide barrier except when the column block (the staged bias) changes.
+// MEASURED (profiles/r2j_ncu_csrb_tma_v1.json, C4 on one B200): 2.68 ms per launch against 1.30 ms for the kernel above.
+// A stage must hold the largest possible item (target + one full segment = 48 KB) but holds 17 KB on average, and only
+// three stages fit beside the 64 KB bias block, so ~32 KB are in flight per SM -- half of what the DRAM latency needs;
+// 43 % of the stall samples are the wait for the bulk copy.  Kept opt-in for the record.
 constexpr int TMA_ROWS = 512;                       // rows per super-chunk: an item never spans more
 constexpr int TMA_TARGET = 4096;                    // entries per item; < TMA_TARGET + CB with the last segment's overshoot
 constexpr int TMA_ENT_BYTES = (TMA_TARGET + CB) * 4;            // 48 KB
@@ -732,9 +736,9 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         h_first[b + 1] = h_first[b] + (int32_t)(e > 0 ? (e + target - 1) / target : 0);
     }
     int nitems = h_first[nb];
-    // HC_CSRB_TMA=0: the register-staged stream kernel with its global queue; default: the TMA-fed kernel, whose items
+    // default: the register-staged stream kernel with its global queue; HC_CSRB_TMA=1: the TMA-fed kernel, whose items
     // are also capped at TMA_ROWS rows and are assigned to the CTAs statically
-    bool tma = true;
+    bool tma = false;       // measured slower (C4, 1 GPU: 2.68 vs 1.30 ms per launch): see DESIGN.md section 4
     if (const char* e = getenv("HC_CSRB_TMA")) tma = atoi(e) != 0;
     int4* d_items = nullptr;
     int32_t* d_first = nullptr;
