@@ -201,67 +201,70 @@ __device__ __forceinline__ void load_tile(const int32_t* __restrict__ X, int64_t
     }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t* sA = reinterpret_cast<int32_t*>(smem_raw);     // [T][T]    tile (I,J)
-    int32_t* sB = sA + T * T;                               // [T][LDB]  tile (J,I)
-    double* sV = reinterpret_cast<double*>(sB + T * LDB);  // PASS_WRITE: [T][LDB] staged mirror tile
-    __shared__ double colred[8][T];
-    __shared__ double red[32];
+// 64 x 64 tile: fast path for tiles that lie inside the matrix (128-bit shared-memory stores, no bound checks)
+__device__ __forceinline__ void load_tile_fast(const int32_t* __restrict__ X, int64_t ld, int r0, int c0, int32_t* dst, int ldd) {
+    const int v = threadIdx.x & 15, rr = threadIdx.x >> 4;
+    int4 x[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) x[a] = ld_stream_v4(X + (int64_t)(r0 + rr + 16 * a) * ld + c0 + 4 * v);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        int32_t* d = dst + (rr + 16 * a) * ldd + 4 * v;
+        if ((ldd & 3) == 0) *reinterpret_cast<int4*>(d) = x[a];
+        else { d[0] = x[a].x; d[1] = x[a].y; d[2] = x[a].z; d[3] = x[a].w; }
+    }
+}
 
-    if (a.ngap_dev) a.has_gap = *a.ngap_dev > 0;
-    int I, J;
-    tile_index(blockIdx.x, a.nT, &I, &J);
-    const int r0 = I * T, c0 = J * T;
-    load_tile(a.X, a.ld, a.n, r0, c0, sA, T);
-    if (I != J) load_tile(a.X, a.ld, a.n, c0, r0, sB, LDB);
-    __syncthreads();
-    const int32_t* tB = (I != J) ? sB : sA;
-    const int ldb = (I != J) ? LDB : T;
-
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps; warp = one tile row at a time
+// The per-cell work of a tile pair.  Everything that depends only on the row or only on the column (1 / alpha, the gap
+// flag, 1 / s) is staged once per tile in shared memory / registers; cells outside the matrix are zero in the staged
+// tiles and have 1 / alpha = 0, so they need no test.  (The first version evaluated bounds, flags and the 1 / alpha
+// loads per cell: 31 thread instructions per cell, issue-bound at 2.6 TB/s -- profiles/r1d_ncu_secondary_raw.csv.)
+template <int PASS, bool GAP>
+__device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, int r0, int c0, const int32_t* sA, const int32_t* tB,
+                                              int ldb, const double* vr, const double* vc, double* sV, double (*colred)[T], double* red) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps; a warp covers one tile row at a time
+    // per-column values of this thread's two columns
+    double raj[2], rsj[2];
+    bool gj[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int c = tx + 32 * b;
+        raj[b] = vc[c];
+        rsj[b] = PASS != PASS_ROWSUM ? vc[T + c] : 0.0;
+        gj[b] = GAP ? vc[2 * T + c] != 0.0 : false;
+    }
     double val[8][2];
-    double rowp[8];
     double colp[2] = {0.0, 0.0};
     double tot = 0.0;
+    const int64_t np = (int64_t)a.nT * T;
 #pragma unroll
     for (int ai = 0; ai < 8; ++ai) {
-        const int r = ty + 8 * ai, gi = r0 + r;
-        const bool vi = gi < a.n;
-        const double ra_i = a.ra[gi];
-        const bool g_i = a.has_gap && vi && a.gapflag[gi];
-        const double rs_i = (PASS != PASS_ROWSUM && vi) ? a.rs[gi] : 0.0;
+        const int r = ty + 8 * ai;
+        const double rai = vr[r];
+        const double rsi = PASS != PASS_ROWSUM ? vr[T + r] : 0.0;
+        const bool gi = GAP ? vr[2 * T + r] != 0.0 : false;
         double rsum = 0.0;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            const int c = tx + 32 * b, gj = c0 + c;
-            const bool vj = gj < a.n;
-            const double ra_j = a.ra[gj];
-            const double sij = i32_to_f64(sA[r * T + c]) * ra_i;
-            const double sji = i32_to_f64(tB[c * ldb + r]) * ra_j;
+            const int c = tx + 32 * b;
+            const double sij = i32_to_f64(sA[r * T + c]) * rai;
+            const double sji = i32_to_f64(tB[c * ldb + r]) * raj[b];
             double sym;
-            if (gi == gj) sym = sij;
-            else if (!a.has_gap) sym = sij + sji;
-            else if (g_i && a.gapflag[vj ? gj : 0]) sym = fmax(sij, sji);
-            else sym = (sij + sji) * 0.5;
-            if (!(vi && vj)) sym = 0.0;
+            if (GAP) sym = (gi && gj[b]) ? fmax(sij, sji) : (sij + sji) * 0.5;
+            else sym = sij + sji;
+            if (I == J && r == c) sym = sij;
             if (PASS == PASS_ROWSUM) { rsum += sym; colp[b] += sym; }
             else {
-                const double cor = sym * (rs_i * (vj ? a.rs[gj] : 0.0));
+                const double cor = sym * (rsi * rsj[b]);
                 if (PASS == PASS_TOTAL) tot += cor; else val[ai][b] = cor;
             }
         }
-        rowp[ai] = rsum;
-    }
-
-    if (PASS == PASS_ROWSUM) {
-        const int64_t np = (int64_t)a.nT * T;
-#pragma unroll
-        for (int ai = 0; ai < 8; ++ai) {
-            const double s = warp_sum(rowp[ai]);
-            if (tx == 0) a.partial[(int64_t)J * np + r0 + ty + 8 * ai] = s;   // rows of block I, other block J
+        if (PASS == PASS_ROWSUM) {
+            const double s = warp_sum(rsum);
+            if (tx == 0) a.partial[(int64_t)J * np + r0 + r] = s;             // rows of block I, other block J
         }
+    }
+    if (PASS == PASS_ROWSUM) {
         if (I != J) {
             colred[ty][tx] = colp[0]; colred[ty][tx + 32] = colp[1];
             __syncthreads();
@@ -282,9 +285,9 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
             const int r = ty + 8 * ai, gi = r0 + r;
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                const int c = tx + 32 * b, gj = c0 + c;
+                const int c = tx + 32 * b, gjj = c0 + c;
                 const double v = rf * val[ai][b];
-                if (gi < a.n && gj < a.n) a.out[(int64_t)gi * a.ld_out + gj] = v;
+                if (gi < a.n && gjj < a.n) a.out[(int64_t)gi * a.ld_out + gjj] = v;
                 if (I != J) sV[c * LDB + r] = v;
             }
         }
@@ -292,15 +295,52 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
             __syncthreads();
 #pragma unroll
             for (int ai = 0; ai < 8; ++ai) {
-                const int c = ty + 8 * ai, gj = c0 + c;   // row of the mirrored tile
+                const int c = ty + 8 * ai, gjj = c0 + c;   // row of the mirrored tile
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const int r = tx + 32 * b, gi = r0 + r;
-                    if (gi < a.n && gj < a.n) a.out[(int64_t)gj * a.ld_out + gi] = sV[c * LDB + r];
+                    if (gi < a.n && gjj < a.n) a.out[(int64_t)gjj * a.ld_out + gi] = sV[c * LDB + r];
                 }
             }
         }
     }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* sA = reinterpret_cast<int32_t*>(smem_raw);     // [T][T]    tile (I,J)
+    int32_t* sB = sA + T * T;                               // [T][LDB]  tile (J,I)
+    double* sV = reinterpret_cast<double*>(sB + T * LDB);  // PASS_WRITE: [T][LDB] staged mirror tile
+    __shared__ double colred[8][T];
+    __shared__ double red[32];
+    __shared__ double vr[3 * T], vc[3 * T];                 // per row / per column of the tile: 1/alpha, 1/s, gap flag
+
+    if (a.ngap_dev) a.has_gap = *a.ngap_dev > 0;
+    int I, J;
+    tile_index(blockIdx.x, a.nT, &I, &J);
+    const int r0 = I * T, c0 = J * T;
+    const bool inside = r0 + T <= a.n && c0 + T <= a.n && c0 + T <= (int)a.ld && r0 + T <= (int)a.ld;
+    if (inside) {
+        load_tile_fast(a.X, a.ld, r0, c0, sA, T);
+        if (I != J) load_tile_fast(a.X, a.ld, c0, r0, sB, LDB);
+    } else {
+        load_tile(a.X, a.ld, a.n, r0, c0, sA, T);
+        if (I != J) load_tile(a.X, a.ld, a.n, c0, r0, sB, LDB);
+    }
+    if (threadIdx.x < 2 * T) {          // ra / rs are zero-padded up to nT * T entries (recip_alpha_kernel, vc_scale_kernel)
+        const int t = threadIdx.x & (T - 1);
+        const int gidx = (threadIdx.x < T ? r0 : c0) + t;
+        double* v = threadIdx.x < T ? vr : vc;
+        v[t] = a.ra[gidx];
+        v[T + t] = PASS != PASS_ROWSUM ? (gidx < a.n ? a.rs[gidx] : 0.0) : 0.0;
+        v[2 * T + t] = (a.has_gap && gidx < a.n && a.gapflag[gidx]) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int32_t* tB = (I != J) ? sB : sA;
+    const int ldb = (I != J) ? LDB : T;
+    if (a.has_gap) sym_pass_body<PASS, true>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red);
+    else sym_pass_body<PASS, false>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red);
 }
 
 __global__ void __launch_bounds__(256) recip_alpha_kernel(SymArgs a) {
