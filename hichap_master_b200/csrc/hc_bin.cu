@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) bin_pairs_band_cluster_kernel(
         if ((int)d < d_hot) {
             const unsigned idx = (unsigned)(grow * d_hot + d);
             const unsigned owner = idx / HOT_PER_CTA, local = idx - owner * HOT_PER_CTA;
-            uint32_t* w = cluster.map_shared_rank(hot, owner) + (local >> 1);
+            uint32_t* w = (csize == 1u ? hot : cluster.map_shared_rank(hot, owner)) + (local >> 1);   // csize 1: plain shared-memory atomic
             const unsigned sh = (local & 1u) * 16u;
             const uint32_t old = atomicAdd(w, 1u << sh);
             if (((old >> sh) & 0xffffu) == 0x7fffu) {          // this add made it 0x8000: drain that much into the band
@@ -516,11 +516,12 @@ extern "C" int hc_bin_band_accumulate(const void* c1, const int32_t* p1, const v
     a.nchrom = nchrom; a.mats = mats; a.mat_off = mat_off; a.mat_n = mat_n; a.mat_ld = mat_ld; a.bin_off = bin_off;
     a.band = reinterpret_cast<int32_t*>(work); a.oob = oob;
     a.bw_shift = band_shift(band_width);
-    // HC_BIN_CLUSTER=N (N = 2, 4, 8 or 16): the hottest diagonals are counted in the distributed shared memory of
-    // clusters of N CTAs (bin_pairs_band_cluster_kernel); 0 = every near-diagonal update is an L2 RED
+    // HC_BIN_CLUSTER=N (N = 1, 2, 4, 8 or 16): the hottest diagonals are counted in the (distributed) shared memory of
+    // clusters of N CTAs (bin_pairs_band_cluster_kernel; N = 1: every CTA keeps its own counters for the main diagonal);
+    // 0 (default) = every near-diagonal update is an L2 RED
     int csize = 0;
     if (const char* e = getenv("HC_BIN_CLUSTER")) csize = atoi(e);
-    if (csize >= 2 && csize <= 16 && (csize & (csize - 1)) == 0 && npairs >= (1 << 20)) {
+    if (csize >= 1 && csize <= 16 && (csize & (csize - 1)) == 0 && npairs >= (1 << 20)) {
         auto kern = chrom_is_u8 ? bin_pairs_band_cluster_kernel<true> : bin_pairs_band_cluster_kernel<false>;
         const size_t smem = (size_t)HOT_PER_CTA * 2;
         HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
