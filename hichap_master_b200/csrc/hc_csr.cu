@@ -7,6 +7,7 @@
 // The reference's upper-triangular (bin1, bin2, count) records (matrixBuilding.py:489-503)
 // are the col >= row subset of this CSR (hc_csr_upper_records).
 #include "hc_common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -182,6 +183,168 @@ csr_upper_emit_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __rest
     }
 }
 
+
+// =========================================================================================
+// One key per pair ("entries"): a 64-bit entry is  (row << (col_bits + cnt_bits)) | (col << cnt_bits) | count.
+// A pair contributes ONE entry of its upper-triangle cell (row <= col, count 1); after the sort and the
+// reduce-by-key the unique upper cells carry their counts in the low bits.  The lower triangle is the same list
+// with row and col swapped: it is already ordered by its new minor key, so a stable LSD sort over the new row
+// bits alone (3 digit passes over the unique cells instead of 5 passes over a second key per pair) orders it, and
+// the symmetric CSR is the row-wise concatenation lower part | upper part of the two lists.
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+pairs_to_entries_kernel(const int32_t* __restrict__ c1, const int32_t* __restrict__ p1, const int32_t* __restrict__ c2,
+                        const int32_t* __restrict__ p2, long long npairs, FastDiv res,
+                        const int64_t* __restrict__ start, const int32_t* __restrict__ chrom_bins, int nchrom,
+                        int cis_only, int col_bits, int cnt_bits, unsigned long long* __restrict__ entries,
+                        unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ oob) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long local_valid = 0, local_oob = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        unsigned long long e = PAD_KEY;
+        const int a = c1[i], b = c2[i];
+        if (a >= 0 && b >= 0 && a < nchrom && b < nchrom && (!cis_only || a == b)) {
+            const int x = p1[i], y = p2[i];
+            const long long ba = x >= 0 ? (long long)fast_div((uint32_t)x, res) : -1;
+            const long long bb = y >= 0 ? (long long)fast_div((uint32_t)y, res) : -1;
+            if (ba < 0 || bb < 0 || ba >= chrom_bins[a] || bb >= chrom_bins[b]) {
+                ++local_oob;
+            } else {
+                const unsigned long long r = (unsigned long long)(ba + start[a]);
+                const unsigned long long c = (unsigned long long)(bb + start[b]);
+                const unsigned long long lo = r < c ? r : c, hi = r < c ? c : r;
+                e = (((lo << col_bits) | hi) << cnt_bits) | 1ull;
+                ++local_valid;
+            }
+        }
+        entries[i] = e;
+    }
+    local_valid = (unsigned long long)warp_sum_ll((long long)local_valid);
+    local_oob = (unsigned long long)warp_sum_ll((long long)local_oob);
+    if ((threadIdx.x & 31) == 0) {
+        if (local_valid) atomicAdd(n_valid, local_valid);
+        if (local_oob && oob) atomicAdd(oob, local_oob);
+    }
+}
+
+// heads per tile on the cell bits (entry >> cnt_bits)
+__global__ void __launch_bounds__(RLE_THREADS)
+ent_count_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_valid_p,
+                 int cnt_bits, int64_t* __restrict__ tile_heads) {
+    __shared__ long long red[32];
+    const long long m = (long long)*n_valid_p;
+    const long long base = (long long)blockIdx.x * RLE_TILE;
+    long long c = 0;
+    for (int j = threadIdx.x; j < RLE_TILE; j += RLE_THREADS) {
+        const long long i = base + j;
+        if (i < m) c += (i == 0) || ((ent[i] >> cnt_bits) != (ent[i - 1] >> cnt_bits));
+    }
+    c = block_sum_ll(c, red);
+    if (threadIdx.x == 0) tile_heads[blockIdx.x] = c;
+}
+
+// position of every head, in order (block-local ordered compaction, like rle_emit_kernel)
+__global__ void __launch_bounds__(RLE_THREADS)
+ent_heads_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_valid_p,
+                 int cnt_bits, const int64_t* __restrict__ tile_off, int64_t* __restrict__ upos) {
+    __shared__ int wtot[RLE_THREADS / 32];
+    __shared__ long long run_s;
+    const long long m = (long long)*n_valid_p;
+    const long long base = (long long)blockIdx.x * RLE_TILE;
+    if (threadIdx.x == 0) run_s = tile_off[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j0 = 0; j0 < RLE_TILE; j0 += RLE_THREADS) {
+        const long long i = base + j0 + threadIdx.x;
+        bool head = false;
+        if (i < m) head = (i == 0) || ((ent[i] >> cnt_bits) != (ent[i - 1] >> cnt_bits));
+        const unsigned b = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) wtot[wid] = __popc(b);
+        __syncthreads();
+        long long off = run_s;
+        for (int w = 0; w < wid; ++w) off += wtot[w];
+        if (head) upos[off + __popc(b & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < RLE_THREADS / 32; ++w) t += wtot[w]; run_s += t; }
+        __syncthreads();
+    }
+}
+
+// one reduced entry per run.  unit != 0: every input count is 1, so the run length is the count; otherwise the
+// counts of the run are added (runs are then short: at most one entry per contributing rank).
+__global__ void __launch_bounds__(256)
+ent_reduce_kernel(const unsigned long long* __restrict__ ent, const int64_t* __restrict__ upos, long long nuniq,
+                  const unsigned long long* __restrict__ n_valid_p, int cnt_bits, int unit,
+                  unsigned long long* __restrict__ out, int32_t* __restrict__ overflow) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nuniq) return;
+    const long long p0 = upos[u], p1 = (u + 1 < nuniq) ? upos[u + 1] : (long long)*n_valid_p;
+    const unsigned long long mask = (1ull << cnt_bits) - 1ull;
+    const unsigned long long e = ent[p0];
+    unsigned long long cnt;
+    if (unit) cnt = (unsigned long long)(p1 - p0);
+    else { cnt = 0; for (long long p = p0; p < p1; ++p) cnt += ent[p] & mask; }
+    if (cnt > mask) { atomicOr(overflow, 1); cnt = mask; }
+    out[u] = (e & ~mask) | cnt;
+}
+
+// swapped copy of the off-diagonal cells; a diagonal cell becomes the padding key (sorts last)
+__global__ void __launch_bounds__(256)
+ent_transpose_kernel(const unsigned long long* __restrict__ up, long long n, int col_bits, int cnt_bits,
+                     unsigned long long* __restrict__ lo, unsigned long long* __restrict__ n_lo) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned long long cmask = (1ull << col_bits) - 1ull, vmask = (1ull << cnt_bits) - 1ull;
+    long long kept = 0;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
+        const unsigned long long e = up[u];
+        const unsigned long long r = e >> (col_bits + cnt_bits), c = (e >> cnt_bits) & cmask;
+        const bool off = r != c;
+        lo[u] = off ? ((((c << col_bits) | r) << cnt_bits) | (e & vmask)) : PAD_KEY;
+        kept += off;
+    }
+    kept = warp_sum_ll(kept);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_lo, (unsigned long long)kept);
+}
+
+// ptr[r] = index of the first entry whose row is >= row0 + r, r in [0, nrows]; *n_p entries (device) or n when n_p == 0
+__global__ void __launch_bounds__(256)
+ent_row_ptr_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_p, long long n_host,
+                   int row_shift, long long row0, long long nrows, int64_t* __restrict__ ptr) {
+    const long long n = n_p ? (long long)*n_p : n_host;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) { for (long long r = t; r <= nrows; r += stride) ptr[r] = 0; return; }
+    for (long long u = t; u < n; u += stride) {
+        const long long row = (long long)(ent[u] >> row_shift) - row0;
+        const long long prev = u == 0 ? -1 : (long long)(ent[u - 1] >> row_shift) - row0;
+        for (long long r = prev + 1; r <= row; ++r) ptr[r] = u;
+        if (u == n - 1) for (long long r = row + 1; r <= nrows; ++r) ptr[r] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ent_row_ptr_sum_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, long long n1, int64_t* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n1) out[r] = a[r] + (b ? b[r] : 0);
+}
+
+// row r of the CSR = lower entries of row r (cols < r, ascending) followed by its upper entries (cols >= r)
+__global__ void __launch_bounds__(256)
+ent_scatter_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_p, long long n_host,
+                   int col_bits, int cnt_bits, long long row0, const int64_t* __restrict__ other_ptr, int other_next,
+                   int32_t* __restrict__ col, int32_t* __restrict__ cnt) {
+    const long long n = n_p ? (long long)*n_p : n_host;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned long long cmask = (1ull << col_bits) - 1ull, vmask = (1ull << cnt_bits) - 1ull;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
+        const unsigned long long e = ent[u];
+        const long long r = (long long)(e >> (col_bits + cnt_bits)) - row0;
+        const long long dst = u + (other_ptr ? other_ptr[r + other_next] : 0);
+        col[dst] = (int32_t)((e >> cnt_bits) & cmask);
+        cnt[dst] = (int32_t)(e & vmask);
+    }
+}
+
 }  // namespace
 
 extern "C" int hc_pairs_to_keys(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
@@ -270,5 +433,119 @@ extern "C" int hc_csr_upper_emit(const int64_t* row_ptr, const int32_t* col, con
     csr_upper_emit_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(row_ptr, col, cnt, row0, nrows, out_ptr,
                                                                              bin1, bin2, val);
     HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+
+// ---- one key per pair: entries -----------------------------------------------------------
+extern "C" int hc_pairs_to_entries(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                                   int64_t npairs, int32_t res, const int64_t* start, const int32_t* chrom_bins,
+                                   int32_t nchrom, int32_t cis_only, int32_t col_bits, int32_t cnt_bits,
+                                   unsigned long long* entries, unsigned long long* n_valid, unsigned long long* oob,
+                                   void* stream) {
+    HC_REQUIRE(npairs >= 0 && res > 0 && nchrom > 0 && col_bits > 0 && cnt_bits > 0 && cnt_bits <= 31 &&
+               2 * col_bits + cnt_bits <= 63, "sizes");
+    HC_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    if (npairs == 0) return HC_OK;
+    long long blocks = (npairs + 255) / 256;
+    const long long cap = (long long)hc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    pairs_to_entries_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        c1, p1, c2, p2, npairs, make_fast_div((uint32_t)res), start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits,
+        entries, n_valid, oob);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+// Distinct cells among the first *n_valid sorted entries -> *h_nuniq (synchronises).  work: hc_csr_work_bytes(n).
+extern "C" int hc_entries_count(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
+                                int32_t cnt_bits, void* work, int64_t* h_nuniq, void* stream) {
+    HC_REQUIRE(n >= 0 && h_nuniq != nullptr && cnt_bits > 0 && cnt_bits < 64, "n>=0, h_nuniq, cnt_bits");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t* tile_heads = reinterpret_cast<int64_t*>(work);
+    const long long tiles = (n + RLE_TILE - 1) / RLE_TILE;
+    *h_nuniq = 0;
+    if (tiles == 0) return HC_OK;
+    ent_count_kernel<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, tile_heads);
+    HC_LAUNCH_CHECK();
+    csr_exclusive_scan_kernel<<<1, 1024, 0, s>>>(tile_heads, tiles);
+    HC_LAUNCH_CHECK();
+    HC_CUDA(cudaMemcpyAsync(h_nuniq, tile_heads + tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return HC_OK;
+}
+
+// Reduced entries out[nuniq] (count = run length when unit, else the sum of the run's counts).  upos: nuniq int64
+// scratch.  *h_overflow = 1 when a count does not fit cnt_bits (synchronises).
+extern "C" int hc_entries_reduce(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
+                                 const void* work, int64_t nuniq, int32_t cnt_bits, int32_t unit, int64_t* upos,
+                                 unsigned long long* out, int32_t* d_overflow, int32_t* h_overflow, void* stream) {
+    HC_REQUIRE(n >= 0 && nuniq >= 0 && d_overflow != nullptr && h_overflow != nullptr, "sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    *h_overflow = 0;
+    if (nuniq == 0) return HC_OK;
+    const long long tiles = (n + RLE_TILE - 1) / RLE_TILE;
+    HC_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
+    ent_heads_kernel<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, reinterpret_cast<const int64_t*>(work), upos);
+    HC_LAUNCH_CHECK();
+    ent_reduce_kernel<<<(unsigned)((nuniq + 255) / 256), 256, 0, s>>>(sorted, upos, nuniq, n_valid, cnt_bits, unit, out, d_overflow);
+    HC_LAUNCH_CHECK();
+    HC_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return HC_OK;
+}
+
+// lo[n]: (col, row, count) of every off-diagonal cell of up[n], padding key for the diagonal ones; *n_lo (device)
+// receives the number of real entries.  Sort lo on bits [cnt_bits + col_bits, cnt_bits + 2*col_bits (+1)) afterwards.
+extern "C" int hc_entries_transpose(const unsigned long long* up, int64_t n, int32_t col_bits, int32_t cnt_bits,
+                                    unsigned long long* lo, unsigned long long* n_lo, void* stream) {
+    HC_REQUIRE(n >= 0 && col_bits > 0 && cnt_bits > 0, "sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    HC_CUDA(cudaMemsetAsync(n_lo, 0, sizeof(unsigned long long), s));
+    if (n == 0) return HC_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)hc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    ent_transpose_kernel<<<(unsigned)blocks, 256, 0, s>>>(up, n, col_bits, cnt_bits, lo, n_lo);
+    HC_LAUNCH_CHECK();
+    return HC_OK;
+}
+
+extern "C" int64_t hc_entries_csr_work_bytes(int64_t nrows) { return (int64_t)sizeof(int64_t) * 2 * (nrows + 1); }
+
+// CSR of the rows [row0, row0+nrows) from the upper list up[n_up] (row <= col, row-major) and the sorted lower list
+// lo[*n_lo] (row > col, row-major); lo == NULL: `up` alone already holds every entry of the rows (row-block shards).
+// row_ptr: nrows+1; col, cnt: n_up + *n_lo.  work: hc_entries_csr_work_bytes(nrows).
+extern "C" int hc_entries_to_csr(const unsigned long long* up, int64_t n_up, const unsigned long long* lo,
+                                 const unsigned long long* n_lo, int32_t col_bits, int32_t cnt_bits, int64_t row0,
+                                 int64_t nrows, void* work, int64_t* row_ptr, int32_t* col, int32_t* cnt, void* stream) {
+    HC_REQUIRE(n_up >= 0 && nrows >= 0 && col_bits > 0 && cnt_bits > 0, "sizes");
+    HC_REQUIRE(lo == nullptr || n_lo != nullptr, "n_lo");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t* up_ptr = reinterpret_cast<int64_t*>(work);
+    int64_t* lo_ptr = up_ptr + (nrows + 1);
+    const int row_shift = col_bits + cnt_bits;
+    const long long cap = (long long)hc_num_sms() * 16;
+    long long blocks = (std::max<long long>(n_up, nrows + 1) + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    ent_row_ptr_kernel<<<(unsigned)blocks, 256, 0, s>>>(up, nullptr, n_up, row_shift, row0, nrows, up_ptr);
+    HC_LAUNCH_CHECK();
+    if (lo) {
+        ent_row_ptr_kernel<<<(unsigned)blocks, 256, 0, s>>>(lo, n_lo, 0, row_shift, row0, nrows, lo_ptr);
+        HC_LAUNCH_CHECK();
+    }
+    ent_row_ptr_sum_kernel<<<(unsigned)((nrows + 1 + 255) / 256), 256, 0, s>>>(up_ptr, lo ? lo_ptr : nullptr, nrows + 1, row_ptr);
+    HC_LAUNCH_CHECK();
+    if (n_up > 0) {
+        // an upper entry of row r sits after the lower entries of the rows <= r
+        ent_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(up, nullptr, n_up, col_bits, cnt_bits, row0, lo ? lo_ptr : nullptr, 1, col, cnt);
+        HC_LAUNCH_CHECK();
+    }
+    if (lo) {
+        // a lower entry of row r sits after the upper entries of the rows < r
+        ent_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(lo, n_lo, 0, col_bits, cnt_bits, row0, up_ptr, 0, col, cnt);
+        HC_LAUNCH_CHECK();
+    }
     return HC_OK;
 }

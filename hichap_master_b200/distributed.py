@@ -44,22 +44,47 @@ def exchange_plan(sorted_rows_hist_local: np.ndarray, cuts):
     return [int(c[cuts[r + 1]] - c[cuts[r]]) for r in range(len(cuts) - 1)]
 
 
-def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only=False):
-    """Collective: returns (SymCsr of this rank's row block, cuts)."""
+def exchange_entry_lists(up, lo, nbins: int):
+    """Collective.  ``up`` / ``lo``: this rank's reduced upper and lower entry lists (int64, each ordered by row).
+    The ranks agree on row boundaries with ~equal numbers of cells and every entry is sent to the owner of its row.
+    Returns (inbox = [upper runs of every rank | lower runs of every rank], cuts).  Works on any backend (the host
+    logic is covered by a gloo test)."""
+    world = dist.get_world_size()
+    dev = up.device
+    cb, cnt_bits = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
+    # rows are the top field of an entry: the first entry of every row is a binary search away.  This bookkeeping,
+    # used to agree on the row boundaries, is the only torch math on the path.
+    edges = torch.arange(nbins + 1, dtype=torch.int64, device=dev) << (cb + cnt_bits)
+    pos_up, pos_lo = torch.searchsorted(up, edges), torch.searchsorted(lo, edges)
+    hist_up, hist_lo = pos_up[1:] - pos_up[:-1], pos_lo[1:] - pos_lo[:-1]
+    # cut on the cells per row (what the owner will store, give or take cells held by several ranks)
+    total = hist_up + hist_lo
+    dist.all_reduce(total)
+    cuts = row_cuts_from_counts(total.cpu().numpy(), world)
+    send_up, send_lo = exchange_plan(hist_up.cpu().numpy(), cuts), exchange_plan(hist_lo.cpu().numpy(), cuts)
+    send_t = torch.tensor([send_up, send_lo], dtype=torch.int64, device=dev).t().contiguous()      # [dest][up, lo]
+    recv_t = torch.empty(world, 2, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_t, send_t)
+    recv = recv_t.cpu().numpy()
+    recv_up, recv_lo = [int(x) for x in recv[:, 0]], [int(x) for x in recv[:, 1]]
+    n_in_up, n_in = sum(recv_up), sum(recv_up) + sum(recv_lo)
+    inbox = torch.empty(n_in, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(inbox[:n_in_up], up.contiguous(), output_split_sizes=recv_up, input_split_sizes=send_up)
+    dist.all_to_all_single(inbox[n_in_up:], lo.contiguous(), output_split_sizes=recv_lo, input_split_sizes=send_lo)
+    return inbox, cuts
+
+
+def _build_row_block_csr_two_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only=False):
+    """First version (two keys per pair, keys exchanged unreduced); HC_SORT_KEYS_PER_PAIR=2 or count-field overflow."""
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = pairs.device
     col_bits = kernels.key_col_bits(nbins)
     skeys, _, n_valid = kernels.pairs_to_sorted_keys(pairs, res, start, chrom_bins, nbins, cis_only)
     m = int(n_valid.item())
     skeys = skeys[:m]
-    # per-row key counts: the keys are sorted, so the first key of every row is a binary search away (nbins searches
-    # instead of a histogram over up to 2 G keys).  This bookkeeping, used to agree on the row boundaries, is the only
-    # torch math on the path.
     edges = torch.arange(nbins + 1, dtype=torch.int64, device=dev) << col_bits
     pos = torch.searchsorted(skeys, edges)                       # first key with row >= r
     hist = pos[1:] - pos[:-1]
-    # cut on DISTINCT keys per row (what a rank will store after reduce-by-key), not on pairs: the many duplicate
-    # pairs next to the diagonal would otherwise skew the cuts (a key held by several ranks is counted once per rank)
     if m > 1:
         first = torch.ones(m, dtype=torch.int32, device=dev)
         first[1:] = (skeys[1:] != skeys[:-1]).to(torch.int32)
@@ -79,9 +104,56 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     recv = [int(x) for x in recv_t.cpu().numpy()]
     inbox = torch.empty(sum(recv), dtype=torch.int64, device=dev)
     dist.all_to_all_single(inbox, skeys.contiguous(), output_split_sizes=recv, input_split_sizes=send)
-    # the received runs are sorted individually: one more radix sort merges them
-    merged, free = kernels.sort_keys_u64(inbox, 2 * col_bits) if inbox.numel() > 1 else (inbox, None)
+    merged, free = kernels.sort_keys_u64(inbox, kernels.key_sort_bits(nbins)) if inbox.numel() > 1 else (inbox, None)
     nv = torch.tensor([merged.numel()], dtype=torch.int64, device=dev)
     row0, row1 = cuts[rank], cuts[rank + 1]
     row_ptr, col, cnt = kernels.keys_to_csr(merged, nv, col_bits, row1 - row0, scratch=free, row0=row0)
+    return kernels.SymCsr(row_ptr, col, cnt, nbins, row0=row0), cuts
+
+
+def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only=False):
+    """Collective: returns (SymCsr of this rank's row block, cuts).
+
+    Every rank reduces ITS pairs to unique upper-triangle cells with counts (one 64-bit entry per cell), derives the
+    lower-triangle list (same cells, row and col swapped, re-sorted on the row bits), and sends each list's rows to
+    their owner; the owner sorts what it received once more and adds the counts of equal cells -- the cells travel
+    reduced, and a row's lower and upper parts interleave into CSR order by that one sort."""
+    import os
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = pairs.device
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    lists = None
+    if os.environ.get("HC_SORT_KEYS_PER_PAIR", "1") == "2":
+        flag += 1
+    else:
+        try:
+            up, sent, free = kernels.pairs_to_upper_entries(pairs, res, start, chrom_bins, nbins, cis_only)
+            lists = (up, sent, free)
+        except kernels.CountFieldOverflow:
+            flag += 1
+    dist.all_reduce(flag)                      # all ranks take the same path
+    if int(flag.item()):
+        del lists
+        return _build_row_block_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only)
+    up, sent, free = lists
+    cb, cnt_bits = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
+    nuniq = int(up.numel())
+    tmp = free[nuniq:] if (free is not None and free.numel() >= 2 * nuniq) else None
+    slo, n_lo = kernels.transpose_entries(up, nbins, lo=sent, tmp=tmp)
+    lo = slo[:int(n_lo.item())]
+    inbox, cuts = exchange_entry_lists(up, lo, nbins)
+    del up, lo, slo, sent, free, tmp
+    merged, mfree = kernels.sort_entries(inbox, nbins, cnt_bits, 2)
+    nv = torch.tensor([inbox.numel()], dtype=torch.int64, device=dev)
+    try:
+        cells = kernels.reduce_entries(merged, nv, nbins, unit=False, scratch=mfree)
+        ok = 0
+    except kernels.CountFieldOverflow:
+        ok = 1
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag)
+    if int(flag.item()):
+        return _build_row_block_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only)
+    row0, row1 = cuts[rank], cuts[rank + 1]
+    row_ptr, col, cnt = kernels.entries_to_csr(cells, None, None, nbins, row1 - row0, row0=row0, total=int(cells.numel()))
     return kernels.SymCsr(row_ptr, col, cnt, nbins, row0=row0), cuts

@@ -378,10 +378,115 @@ def pairs_to_sorted_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins:
     return skeys, free, n_valid
 
 
-def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
-                 check_bounds=True) -> SymCsr:
-    """Binning through the sort path (north_star kernel (a)): every pair becomes one or two
-    (row, col) keys, the keys are radix-sorted and run-length reduced into a symmetric CSR."""
+def entry_cnt_bits(nbins: int) -> int:
+    """Width of the count field of a 64-bit entry (row | col | count): what two column fields and the
+    padding bit leave, at most 31 (counts are int32 in the CSR)."""
+    room = min(31, 63 - 2 * key_col_bits(nbins))
+    return min(room, int(os.environ.get("HC_ENTRY_CNT_BITS", room)))       # the variable is a test hook
+
+
+def sort_entries(ent, nbins: int, begin_bit: int, nfields: int, tmp=None):
+    """Stable radix sort of entries on ``nfields`` bin fields starting at ``begin_bit`` (plus the bit above them
+    when nbins is a power of two, so that the padding key ~0 sorts strictly last)."""
+    cb = key_col_bits(nbins)
+    end_bit = begin_bit + nfields * cb + (1 if int(nbins) == (1 << cb) else 0)
+    n = int(ent.numel())
+    if n <= 1:
+        return ent, tmp
+    if tmp is None:
+        tmp = torch.empty_like(ent)
+    work = torch.empty(int(lib().hc_sort_work_bytes(n)), dtype=torch.uint8, device=ent.device)
+    in_tmp = C.c_int32(0)
+    check(lib().hc_sort_keys_u64(ptr(ent), ptr(tmp), n, int(begin_bit), int(end_bit), ptr(work), C.byref(in_tmp),
+                                 stream_ptr()), "hc_sort_keys_u64")
+    return (tmp, ent) if in_tmp.value else (ent, tmp)
+
+
+class CountFieldOverflow(OverflowError):
+    """A cell count does not fit the count field of the 64-bit entries."""
+
+
+def reduce_entries(sorted_ent, n_valid, nbins: int, unit: bool, scratch=None):
+    """Reduce-by-cell over sorted entries -> reduced entries [nuniq].  ``scratch``: optional int64 tensor that
+    receives the result (and, behind it, the head positions) when it is large enough."""
+    dev, n = sorted_ent.device, int(sorted_ent.numel())
+    cnt_bits = entry_cnt_bits(nbins)
+    work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=dev)
+    nuniq = C.c_int64(0)
+    check(lib().hc_entries_count(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), C.byref(nuniq), stream_ptr()),
+          "hc_entries_count")
+    nuniq = int(nuniq.value)
+    room = int(scratch.numel()) if scratch is not None else 0
+    out = scratch[:nuniq] if room >= nuniq else torch.empty(nuniq, dtype=torch.int64, device=dev)
+    upos = scratch[nuniq:2 * nuniq] if room >= 2 * nuniq else torch.empty(max(nuniq, 1), dtype=torch.int64, device=dev)
+    d_ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    h_ovf = C.c_int32(0)
+    check(lib().hc_entries_reduce(ptr(sorted_ent), n, ptr(n_valid), ptr(work), nuniq, cnt_bits, int(bool(unit)), ptr(upos),
+                                  ptr(out), ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce")
+    if h_ovf.value:
+        raise CountFieldOverflow("a cell holds more than 2^%d - 1 pairs" % cnt_bits)
+    return out
+
+
+def pairs_to_upper_entries(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                           check_bounds=True):
+    """pairs -> one entry per pair (its upper-triangle cell) -> sorted -> reduced.  Returns
+    (up [nuniq] ordered by (row, col), two free int64 scratch tensors of >= pairs.n elements in total)."""
+    dev = pairs.device
+    cb, cnt_bits = key_col_bits(nbins), entry_cnt_bits(nbins)
+    ent = torch.empty(max(pairs.n, 1), dtype=torch.int64, device=dev)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+    oob = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().hc_pairs_to_entries(ptr(pairs.c1), ptr(pairs.p1), ptr(pairs.c2), ptr(pairs.p2), pairs.n, int(res),
+                                    ptr(start), ptr(chrom_bins), int(start.numel()), int(bool(cis_only)), cb, cnt_bits,
+                                    ptr(ent), ptr(n_valid), ptr(oob), stream_ptr()), "hc_pairs_to_entries")
+    if check_bounds:
+        _raise_oob(oob, "genome-wide")
+    ent = ent[:pairs.n]
+    sent, free = sort_entries(ent, nbins, cnt_bits, 2)
+    # the reduced list goes into the free half of the ping-pong pair, the head positions behind it when they fit
+    up = reduce_entries(sent, n_valid, nbins, unit=True, scratch=free)
+    return up, sent, free
+
+
+def entries_to_csr(up, lo, n_lo, nbins: int, nrows: int, row0: int = 0, total=None):
+    """Symmetric CSR tensors (row_ptr, col, cnt) from the upper list and (optionally) the sorted lower list."""
+    dev = up.device
+    cb, cnt_bits = key_col_bits(nbins), entry_cnt_bits(nbins)
+    n_up = int(up.numel())
+    if total is None:
+        total = n_up + (int(n_lo.item()) if lo is not None else 0)
+    row_ptr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(total, dtype=torch.int32, device=dev)
+    cnt = torch.empty(total, dtype=torch.int32, device=dev)
+    work = torch.empty(int(lib().hc_entries_csr_work_bytes(nrows)), dtype=torch.uint8, device=dev)
+    check(lib().hc_entries_to_csr(ptr(up), n_up, ptr(lo) if lo is not None else None, ptr(n_lo) if lo is not None else None,
+                                  cb, cnt_bits, int(row0), int(nrows), ptr(work), ptr(row_ptr), ptr(col), ptr(cnt),
+                                  stream_ptr()), "hc_entries_to_csr")
+    return row_ptr, col, cnt
+
+
+def transpose_entries(up, nbins: int, lo=None, tmp=None):
+    """Lower-triangle list of an upper list: swapped entries, sorted by (row, col).  Returns (lo_sorted, n_lo device
+    scalar); the diagonal cells end up as padding keys behind the first n_lo entries."""
+    dev, n = up.device, int(up.numel())
+    cb, cnt_bits = key_col_bits(nbins), entry_cnt_bits(nbins)
+    if lo is None or lo.numel() < n:
+        lo = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    lo = lo[:n]
+    n_lo = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().hc_entries_transpose(ptr(up), n, cb, cnt_bits, ptr(lo), ptr(n_lo), stream_ptr()), "hc_entries_transpose")
+    if tmp is not None:
+        tmp = tmp[:n] if tmp.numel() >= n else None
+    slo, _ = sort_entries(lo, nbins, cnt_bits + cb, 1, tmp=tmp)
+    return slo, n_lo
+
+
+def _pairs_to_csr_two_keys(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                           check_bounds=True) -> SymCsr:
+    """The first version of the sort path: two keys per off-diagonal pair, five digit passes over all of them.
+    Kept as the fallback for counts that overflow the entry count field and for A/B measurements
+    (HC_SORT_KEYS_PER_PAIR=2)."""
     dev = pairs.device
     col_bits = key_col_bits(nbins)
     keys = torch.empty(2 * max(pairs.n, 1), dtype=torch.int64, device=dev)
@@ -397,6 +502,26 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
     # (rounded up to whole 8-bit digits) leaves the real keys first and in order
     skeys, free = sort_keys_u64(keys, key_sort_bits(nbins)) if pairs.n else (keys, None)
     row_ptr, col, cnt = keys_to_csr(skeys, n_valid, col_bits, nbins, scratch=free)
+    return SymCsr(row_ptr, col, cnt, nbins)
+
+
+def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                 check_bounds=True) -> SymCsr:
+    """Binning through the sort path (north_star kernel (a)): every pair becomes ONE 64-bit entry of its
+    upper-triangle cell; the entries are radix-sorted and reduced by cell; the lower triangle is the swapped list
+    re-sorted on its row bits only; the symmetric CSR is the row-wise concatenation of the two lists."""
+    if os.environ.get("HC_SORT_KEYS_PER_PAIR", "1") == "2" or pairs.n == 0:
+        return _pairs_to_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
+    try:
+        up, sent, free = pairs_to_upper_entries(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
+    except CountFieldOverflow:
+        return _pairs_to_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
+    nuniq = int(up.numel())
+    # `sent` (the sorted pair entries) is dead now: it holds the lower list; the ping-pong partner of the second sort
+    # is the part of `free` behind the upper list when it is long enough
+    tmp = free[nuniq:] if (free is not None and free.numel() >= 2 * nuniq) else None
+    slo, n_lo = transpose_entries(up, nbins, lo=sent, tmp=tmp)
+    row_ptr, col, cnt = entries_to_csr(up, slo, n_lo, nbins, nbins)
     return SymCsr(row_ptr, col, cnt, nbins)
 
 

@@ -255,6 +255,39 @@ int hc_csr_emit(const unsigned long long* sorted_keys, int64_t nkeys, const unsi
                 unsigned long long* ukey,
                 int64_t* upos, int64_t* row_ptr, int32_t* col, int32_t* cnt, void* stream);
 
+/* One key per pair (the default sort path).  A 64-bit ENTRY is
+ *   (row << (col_bits + cnt_bits)) | (col << cnt_bits) | count,   2*col_bits + cnt_bits <= 63.
+ * hc_pairs_to_entries writes one entry per pair: its upper-triangle cell (row <= col) with count 1, or the padding
+ * key ~0 for a dropped pair (npairs entries; *n_valid, *oob as in hc_pairs_to_keys).  After hc_sort_keys_u64 on the
+ * bits [cnt_bits, cnt_bits + 2*col_bits (+1 when nbins is a power of two)):
+ *   hc_entries_count     distinct cells among the first *n_valid entries -> *h_nuniq (synchronises);
+ *   hc_entries_reduce    out[nuniq] = one entry per cell; unit != 0: count = run length (all inputs carry 1),
+ *                        unit == 0: the counts of a run are added (merging lists received from other ranks).
+ *                        *h_overflow = 1 when a count needs more than cnt_bits bits (synchronises);
+ *   hc_entries_transpose lo[n] = the off-diagonal cells with row and col swapped (padding key for diagonal cells),
+ *                        *n_lo (device) = number of real ones.  `up` is ordered by (row, col), so lo is already
+ *                        ordered by its minor key: ONE stable sort over the new row bits
+ *                        [cnt_bits + col_bits, cnt_bits + 2*col_bits (+1)) orders it;
+ *   hc_entries_to_csr    symmetric CSR of the rows [row0, row0+nrows): row r = lower entries | upper entries.
+ *                        lo == NULL: `up` holds every entry of those rows (a row-block shard after the exchange).
+ * Replaces the same reference lines as hc_pairs_to_keys (matrixBuilding.py:559-603). */
+int hc_pairs_to_entries(const int32_t* c1, const int32_t* p1, const int32_t* c2, const int32_t* p2,
+                        int64_t npairs, int32_t res, const int64_t* start, const int32_t* chrom_bins,
+                        int32_t nchrom, int32_t cis_only, int32_t col_bits, int32_t cnt_bits,
+                        unsigned long long* entries, unsigned long long* n_valid, unsigned long long* oob,
+                        void* stream);
+int hc_entries_count(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
+                     int32_t cnt_bits, void* work /* hc_csr_work_bytes(n) */, int64_t* h_nuniq, void* stream);
+int hc_entries_reduce(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
+                      const void* work, int64_t nuniq, int32_t cnt_bits, int32_t unit, int64_t* upos /* nuniq */,
+                      unsigned long long* out, int32_t* d_overflow, int32_t* h_overflow, void* stream);
+int hc_entries_transpose(const unsigned long long* up, int64_t n, int32_t col_bits, int32_t cnt_bits,
+                         unsigned long long* lo, unsigned long long* n_lo, void* stream);
+int64_t hc_entries_csr_work_bytes(int64_t nrows);
+int hc_entries_to_csr(const unsigned long long* up, int64_t n_up, const unsigned long long* lo,
+                      const unsigned long long* n_lo, int32_t col_bits, int32_t cnt_bits, int64_t row0,
+                      int64_t nrows, void* work, int64_t* row_ptr, int32_t* col, int32_t* cnt, void* stream);
+
 /* Upper-triangular (bin1, bin2, count) records of the symmetric CSR in row-major order
  * (WholeMatrixToSparseDict's output layout before the per-chromosome split): count fills
  * out_ptr[nrows+1] (exclusive scan), then emit. */

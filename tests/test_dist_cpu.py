@@ -109,3 +109,58 @@ def test_row_block_sharded_ice_world2_gloo():
     for p in procs:
         p.join(30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _entries_worker(rank, world, port, out):
+    """Host logic of build_row_block_csr's exchange on gloo: reduced upper / lower entry lists per rank ->
+    exchange_entry_lists -> (numpy stand-in for the sort + add-counts reduce) == the owner's rows of the full matrix."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hichap_master_b200 import kernels
+        from hichap_master_b200.distributed import exchange_entry_lists
+        g = load_golden("ice_restated.npz")
+        n = int(g["chrom_offsets"][-1])
+        b1, b2, cnt = g["gw_bin1"].astype(np.int64), g["gw_bin2"].astype(np.int64), g["gw_count"].astype(np.int64)
+        cb, vb = kernels.key_col_bits(n), kernels.entry_cnt_bits(n)
+        assert 2 * cb + vb <= 63
+        # every rank holds a share of each cell's pairs (cells are split unevenly, some only on one rank)
+        rng = np.random.default_rng(5)
+        share = rng.integers(0, cnt + 1) if world == 2 else cnt
+        mine = share if rank == 0 else cnt - share
+        keep = mine > 0
+        r, c, v = b1[keep], b2[keep], mine[keep]
+        up = np.sort(((r << cb | c) << vb) | v)
+        offd = r != c
+        lo = np.sort((((c[offd] << cb) | r[offd]) << vb) | v[offd])
+        inbox, cuts = exchange_entry_lists(torch.from_numpy(up), torch.from_numpy(lo), n)
+        e = np.sort(inbox.numpy())
+        cell, val = e >> vb, e & ((1 << vb) - 1)
+        ucell, inv = np.unique(cell, return_inverse=True)
+        uval = np.bincount(inv, weights=val).astype(np.int64) if cell.size else np.zeros(0, np.int64)
+        # expected: rows [cuts[rank], cuts[rank+1]) of the symmetric matrix
+        R = np.concatenate([b1, b2[b1 != b2]]); Cc = np.concatenate([b2, b1[b1 != b2]]); V = np.concatenate([cnt, cnt[b1 != b2]])
+        sel = (R >= cuts[rank]) & (R < cuts[rank + 1])
+        o = np.lexsort((Cc[sel], R[sel]))
+        assert np.array_equal(ucell, ((R[sel] << cb) | Cc[sel])[o])
+        assert np.array_equal(uval, V[sel][o])
+        assert cuts[0] == 0 and cuts[-1] == n
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_entry_list_exchange_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_entries_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

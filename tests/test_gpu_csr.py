@@ -49,9 +49,13 @@ def small_case(seed, n_pairs, trans):
     return genome, order, c1, p1, c2, p2
 
 
+@pytest.mark.parametrize("keys_per_pair", ["1", "2"])
 @pytest.mark.parametrize("res,cis_only,npairs", [(40000, False, 60_000), (40000, True, 60_000), (500000, False, 5_000),
                                                  (10000, False, 7), (40000, False, 0)])
-def test_pairs_to_csr_matches_oracle(K, cuda_device, res, cis_only, npairs):
+def test_pairs_to_csr_matches_oracle(K, cuda_device, monkeypatch, res, cis_only, npairs, keys_per_pair):
+    """keys_per_pair=1: the default (one upper-triangle entry per pair, lower list by a row-bits re-sort);
+    2: the first version (both orientations sorted)."""
+    monkeypatch.setenv("HC_SORT_KEYS_PER_PAIR", keys_per_pair)
     from hichap_master_b200 import matrixBuilding as mb
     from hichap_master_b200.device import PairColumns
     genome, order, c1, p1, c2, p2 = small_case(5, max(npairs, 1), 0.2)
@@ -220,3 +224,83 @@ def test_ice_csr_count_beyond_19_bits_uses_the_row_major_kernel(K, cuda_device):
     ref, rst = cooler_ice.balance(b1, b2, cnt, n, np.array([0, n]), cis_only=False)
     check_weights(bias.cpu().numpy(), ref, "count overflow fallback")
     assert st["iters"] == rst["iters"]
+
+
+def _random_pairs_one_chrom(nb, res, npairs, seed, hot=0.0):
+    rng = np.random.default_rng(seed)
+    p1 = rng.integers(0, nb * res, npairs).astype(np.int32)
+    p2 = np.clip(p1 + rng.integers(-30 * res, 30 * res, npairs), 0, nb * res - 1).astype(np.int32)
+    if hot:                                                 # a heavy cell
+        k = int(hot * npairs)
+        p1[:k] = 5 * res + 1; p2[:k] = 9 * res + 3
+    return np.zeros(npairs, np.int32), p1, p2
+
+
+@pytest.mark.parametrize("nb", [1024, 777, 1])
+def test_entry_path_equals_two_key_path(K, cuda_device, monkeypatch, nb):
+    """Same symmetric CSR from both versions of the sort path, incl. a power-of-two bin count (padding-bit case)
+    and dropped pairs (padding keys in the middle of the list)."""
+    import torch
+    from hichap_master_b200.device import PairColumns
+    res = 1000
+    c1, p1, p2 = _random_pairs_one_chrom(nb, res, 300_000, nb)
+    c1[::11] = -1                                           # filtered chromosome -> padding entries
+    p1[7::13] = nb * res - 1; p2[7::13] = nb * res - 1      # the last diagonal cell (all-ones key when nb is 2^k)
+    start = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    chrom_bins = torch.tensor([nb], dtype=torch.int32, device=cuda_device)
+    out = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("HC_SORT_KEYS_PER_PAIR", mode)
+        csr = K.pairs_to_csr(PairColumns(c1, p1, c1, p2, device=cuda_device), res, start, chrom_bins, nb, False)
+        out[mode] = [t.cpu().numpy() for t in (csr.row_ptr, csr.col, csr.cnt)]
+    for a, b in zip(out["1"], out["2"]):
+        assert np.array_equal(a, b)
+    keep = c1 >= 0
+    M = np.zeros((nb, nb), np.int64)
+    np.add.at(M, (p1[keep] // res, p2[keep] // res), 1)
+    M = M + M.T - np.diag(np.diag(M))
+    x, y = np.nonzero(M)
+    assert np.array_equal(out["1"][1], y) and np.array_equal(out["1"][2], M[x, y])
+    assert np.array_equal(np.repeat(np.arange(nb), np.diff(out["1"][0])), x)
+
+
+def test_entry_count_field_overflow_falls_back(K, cuda_device, monkeypatch):
+    """A cell with more pairs than the count field holds: the entry path reports it and the two-key path (run lengths
+    as int32 counts, no field limit) produces the matrix."""
+    import torch
+    from hichap_master_b200.device import PairColumns
+    monkeypatch.setenv("HC_ENTRY_CNT_BITS", "6")            # test hook: 63 pairs per cell at most
+    nb, res = 300, 1000
+    c1, p1, p2 = _random_pairs_one_chrom(nb, res, 40_000, 3, hot=0.05)
+    start = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    chrom_bins = torch.tensor([nb], dtype=torch.int32, device=cuda_device)
+    pairs = PairColumns(c1, p1, c1, p2, device=cuda_device)
+    with pytest.raises(K.CountFieldOverflow):
+        K.pairs_to_upper_entries(pairs, res, start, chrom_bins, nb, False)
+    csr = K.pairs_to_csr(pairs, res, start, chrom_bins, nb, False)
+    M = np.zeros((nb, nb), np.int64)
+    np.add.at(M, (p1 // res, p2 // res), 1)
+    M = M + M.T - np.diag(np.diag(M))
+    x, y = np.nonzero(M)
+    assert M.max() > 63
+    assert np.array_equal(csr.col.cpu().numpy(), y) and np.array_equal(csr.cnt.cpu().numpy(), M[x, y])
+
+
+def test_reduce_entries_adds_counts(K, cuda_device):
+    """unit=False (merging lists from several ranks): counts of equal cells are added."""
+    import torch
+    nb = 5000
+    cb, vb = K.key_col_bits(nb), K.entry_cnt_bits(nb)
+    rng = np.random.default_rng(9)
+    cells = rng.integers(0, nb * 40, 200_000)
+    r, c = cells // 40, np.minimum(cells // 40 + cells % 40, nb - 1)
+    v = rng.integers(1, 1000, cells.size)
+    ent = (((r << cb) | c) << vb) | v
+    t = torch.from_numpy(ent.astype(np.int64)).to(cuda_device)
+    sent, free = K.sort_entries(t, nb, vb, 2)
+    nv = torch.tensor([ent.size], dtype=torch.int64, device=cuda_device)
+    got = K.reduce_entries(sent, nv, nb, unit=False, scratch=free).cpu().numpy()
+    key = (r << cb) | c
+    uk, inv = np.unique(key, return_inverse=True)
+    tot = np.bincount(inv, weights=v).astype(np.int64)
+    assert np.array_equal(got >> vb, uk) and np.array_equal(got & ((1 << vb) - 1), tot)
