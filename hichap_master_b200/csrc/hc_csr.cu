@@ -192,6 +192,24 @@ csr_upper_emit_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __rest
 // bits alone (3 digit passes over the unique cells instead of 5 passes over a second key per pair) orders it, and
 // the symmetric CSR is the row-wise concatenation lower part | upper part of the two lists.
 // =========================================================================================
+__device__ __forceinline__ unsigned long long pair_entry(int a, int x, int b, int y, FastDiv res, const int64_t* __restrict__ start,
+                                                        const int32_t* __restrict__ chrom_bins, int nchrom, int cis_only,
+                                                        int col_bits, int cnt_bits, unsigned long long& n_valid,
+                                                        unsigned long long& n_oob) {
+    if (a < 0 || b < 0 || a >= nchrom || b >= nchrom || (cis_only && a != b)) return PAD_KEY;
+    const long long ba = x >= 0 ? (long long)fast_div((uint32_t)x, res) : -1;
+    const long long bb = y >= 0 ? (long long)fast_div((uint32_t)y, res) : -1;
+    if (ba < 0 || bb < 0 || ba >= chrom_bins[a] || bb >= chrom_bins[b]) { ++n_oob; return PAD_KEY; }
+    const unsigned long long r = (unsigned long long)(ba + start[a]);
+    const unsigned long long c = (unsigned long long)(bb + start[b]);
+    const unsigned long long lo = r < c ? r : c, hi = r < c ? c : r;
+    ++n_valid;
+    return (((lo << col_bits) | hi) << cnt_bits) | 1ull;
+}
+
+// VEC: four pairs per thread and trip through 128-bit loads (64 B of loads in flight per thread; one pair per trip left the
+// kernel at 2.5 TB/s); needs 16-byte aligned columns, checked by the launcher.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 pairs_to_entries_kernel(const int32_t* __restrict__ c1, const int32_t* __restrict__ p1, const int32_t* __restrict__ c2,
                         const int32_t* __restrict__ p2, long long npairs, FastDiv res,
@@ -199,26 +217,26 @@ pairs_to_entries_kernel(const int32_t* __restrict__ c1, const int32_t* __restric
                         int cis_only, int col_bits, int cnt_bits, unsigned long long* __restrict__ entries,
                         unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ oob) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long local_valid = 0, local_oob = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
-        unsigned long long e = PAD_KEY;
-        const int a = c1[i], b = c2[i];
-        if (a >= 0 && b >= 0 && a < nchrom && b < nchrom && (!cis_only || a == b)) {
-            const int x = p1[i], y = p2[i];
-            const long long ba = x >= 0 ? (long long)fast_div((uint32_t)x, res) : -1;
-            const long long bb = y >= 0 ? (long long)fast_div((uint32_t)y, res) : -1;
-            if (ba < 0 || bb < 0 || ba >= chrom_bins[a] || bb >= chrom_bins[b]) {
-                ++local_oob;
-            } else {
-                const unsigned long long r = (unsigned long long)(ba + start[a]);
-                const unsigned long long c = (unsigned long long)(bb + start[b]);
-                const unsigned long long lo = r < c ? r : c, hi = r < c ? c : r;
-                e = (((lo << col_bits) | hi) << cnt_bits) | 1ull;
-                ++local_valid;
-            }
+    long long done = 0;
+    if (VEC) {
+        const long long nvec = npairs >> 2;
+        for (long long v = t; v < nvec; v += stride) {
+            const int4 a = ld_stream_v4(c1 + 4 * v), x = ld_stream_v4(p1 + 4 * v), b = ld_stream_v4(c2 + 4 * v), y = ld_stream_v4(p2 + 4 * v);
+            ulonglong2 e0, e1;
+            e0.x = pair_entry(a.x, x.x, b.x, y.x, res, start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits, local_valid, local_oob);
+            e0.y = pair_entry(a.y, x.y, b.y, y.y, res, start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits, local_valid, local_oob);
+            e1.x = pair_entry(a.z, x.z, b.z, y.z, res, start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits, local_valid, local_oob);
+            e1.y = pair_entry(a.w, x.w, b.w, y.w, res, start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits, local_valid, local_oob);
+            reinterpret_cast<ulonglong2*>(entries)[2 * v] = e0;
+            reinterpret_cast<ulonglong2*>(entries)[2 * v + 1] = e1;
         }
-        entries[i] = e;
+        done = nvec << 2;
     }
+    for (long long i = done + t; i < npairs; i += stride)
+        entries[i] = pair_entry(c1[i], p1[i], c2[i], p2[i], res, start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits,
+                                local_valid, local_oob);
     local_valid = (unsigned long long)warp_sum_ll((long long)local_valid);
     local_oob = (unsigned long long)warp_sum_ll((long long)local_oob);
     if ((threadIdx.x & 31) == 0) {
@@ -447,12 +465,19 @@ extern "C" int hc_pairs_to_entries(const int32_t* c1, const int32_t* p1, const i
                2 * col_bits + cnt_bits <= 63, "sizes");
     HC_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     if (npairs == 0) return HC_OK;
-    long long blocks = (npairs + 255) / 256;
+    long long blocks = (npairs / 4 + 255) / 256 + 1;
     const long long cap = (long long)hc_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    pairs_to_entries_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        c1, p1, c2, p2, npairs, make_fast_div((uint32_t)res), start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits,
-        entries, n_valid, oob);
+    const bool vec = ((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(c2) |
+                       reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(entries)) & 15) == 0;
+    if (vec)
+        pairs_to_entries_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            c1, p1, c2, p2, npairs, make_fast_div((uint32_t)res), start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits,
+            entries, n_valid, oob);
+    else
+        pairs_to_entries_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            c1, p1, c2, p2, npairs, make_fast_div((uint32_t)res), start, chrom_bins, nchrom, cis_only, col_bits, cnt_bits,
+            entries, n_valid, oob);
     HC_LAUNCH_CHECK();
     return HC_OK;
 }

@@ -140,6 +140,178 @@ ice_filter_mad_kernel(const double* __restrict__ marg, int64_t nbins, double mad
         if (marg[i] < cutoff) bias[i] = 0.0;
 }
 
+// ---- the same filter over the whole grid -------------------------------------------------
+// One CTA streaming 2 x 8 radix passes over all bins is latency-bound (0.5 ms at 62 k bins, ~3 ms at 304 k).  Here every
+// pass is one grid-wide launch: CTAs histogram their share into shared memory, add it to a global histogram, and the
+// last CTA to finish picks the digit (last-block pattern) -- ~20 short launches whatever the number of bins.
+struct MadState {
+    unsigned long long prefix, mask;    // radix-select state: keys with (key & mask) == prefix are still candidates
+    long long k;                        // rank of the wanted key among the candidates
+    long long count;                    // valid (positive-marginal) bins
+    long long le;                       // keys <= the selected key
+    unsigned long long nxt;             // smallest key above the selected key
+    unsigned int done;                  // CTAs that finished the current launch
+    unsigned int pad;
+    unsigned int hist[256];
+    double result[2];                   // median of the log-marginals, median absolute deviation
+};
+constexpr unsigned long long MAD_INVALID = ~0ull;    // not the key of any finite value
+constexpr int MAD_THREADS = 256;
+
+__device__ __forceinline__ long long mad_median_rank(long long count) { return (count & 1) ? count / 2 : count / 2 - 1; }
+
+// last-block pattern: true in every thread of the CTA that finishes last
+__device__ __forceinline__ bool mad_last_cta(MadState* st, int* flag_s) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&st->done, 1u);
+        *flag_s = (t == gridDim.x - 1);
+        if (*flag_s) st->done = 0;
+    }
+    __syncthreads();
+    const bool last = *flag_s != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// stage 0: keys of log(marg) for marg > 0 (lg keeps the logs); stage 1: keys of |lg - median|
+template <int STAGE>
+__global__ void __launch_bounds__(MAD_THREADS)
+mad_keys_kernel(const double* __restrict__ marg, long long n, double* __restrict__ lg, unsigned long long* __restrict__ keys,
+                MadState* st) {
+    __shared__ long long red[32];
+    const double med = STAGE ? *reinterpret_cast<volatile double*>(&st->result[0]) : 0.0;
+    long long cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = marg[i];
+        const bool ok = v > 0.0;            // false for NaN
+        unsigned long long key = MAD_INVALID;
+        if (STAGE == 0) {
+            const double l = ok ? log(v) : 0.0;
+            lg[i] = l;
+            if (ok) key = f64_key(l);
+        } else if (ok) {
+            key = f64_key(fabs(__dadd_rn(lg[i], -med)));
+        }
+        keys[i] = key;
+        cnt += ok;
+    }
+    if (STAGE == 0) {
+        cnt = block_sum_ll(cnt, red);
+        if (threadIdx.x == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&st->count), (unsigned long long)cnt);
+    }
+}
+
+// one 8-bit digit of the radix select (shift = 56, 48, .. 0)
+__global__ void __launch_bounds__(MAD_THREADS)
+mad_select_pass_kernel(const unsigned long long* __restrict__ keys, long long n, int shift, MadState* st) {
+    __shared__ unsigned int hist[256];
+    __shared__ int flag_s;
+    const long long count = *reinterpret_cast<volatile long long*>(&st->count);
+    if (count == 0) return;
+    const bool first = shift == 56;
+    const unsigned long long prefix = first ? 0ull : *reinterpret_cast<volatile unsigned long long*>(&st->prefix);
+    const unsigned long long mask = first ? 0ull : *reinterpret_cast<volatile unsigned long long*>(&st->mask);
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const long long i = base + u * stride; key[u] = i < n ? keys[i] : MAD_INVALID; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (key[u] != MAD_INVALID && (key[u] & mask) == prefix) atomicAdd(&hist[(key[u] >> shift) & 255ull], 1u);
+    }
+    __syncthreads();
+    if (hist[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], hist[threadIdx.x]);
+    if (!mad_last_cta(st, &flag_s)) return;
+    // the last CTA: warp 0 finds the digit that holds rank k (lane l owns digits 8l .. 8l+7)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        long long k = first ? mad_median_rank(count) : *reinterpret_cast<volatile long long*>(&st->k);
+        unsigned int h[8];
+        long long s = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { h[e] = __ldcg(&st->hist[8 * lane + e]); s += h[e]; }
+        long long incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        long long run = incl - s;
+        if (k >= run && k < incl) {
+            int digit = 8 * lane + 7;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (k < run + h[e]) { digit = 8 * lane + e; break; }
+                if (e < 7) run += h[e];
+            }
+            st->prefix = prefix | ((unsigned long long)digit << shift);
+            st->mask = mask | (0xffull << shift);
+            st->k = k - run;
+            if (shift == 0) { st->le = 0; st->nxt = MAD_INVALID; }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) st->hist[8 * lane + e] = 0;
+    }
+}
+
+// neighbours of the selected key -> the median (NumPy: mean of the two middle values for an even count)
+template <int STAGE>
+__global__ void __launch_bounds__(MAD_THREADS)
+mad_median_kernel(const unsigned long long* __restrict__ keys, long long n, MadState* st) {
+    __shared__ long long red[32];
+    __shared__ unsigned long long redu[32];
+    __shared__ int flag_s;
+    const long long count = *reinterpret_cast<volatile long long*>(&st->count);
+    if (count == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->result[STAGE] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    const unsigned long long klo = *reinterpret_cast<volatile unsigned long long*>(&st->prefix);
+    long long le = 0;
+    unsigned long long nxt = MAD_INVALID;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        if (key == MAD_INVALID) continue;
+        if (key <= klo) ++le; else if (key < nxt) nxt = key;
+    }
+    le = block_sum_ll(le, red);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, nxt, o);
+        nxt = other < nxt ? other : nxt;
+    }
+    if ((threadIdx.x & 31) == 0) redu[threadIdx.x >> 5] = nxt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < MAD_THREADS / 32; ++w) nxt = redu[w] < nxt ? redu[w] : nxt;
+        if (le) atomicAdd(reinterpret_cast<unsigned long long*>(&st->le), (unsigned long long)le);
+        atomicMin(&st->nxt, nxt);
+    }
+    if (!mad_last_cta(st, &flag_s)) return;
+    if (threadIdx.x == 0) {
+        const long long k = mad_median_rank(count);
+        const long long le_all = *reinterpret_cast<volatile long long*>(&st->le);
+        const unsigned long long nxt_all = *reinterpret_cast<volatile unsigned long long*>(&st->nxt);
+        const double lo = key_f64(klo);
+        double hi = lo;
+        if (k + 1 < count && le_all < k + 2) hi = key_f64(nxt_all);
+        st->result[STAGE] = (count & 1) ? lo : __dmul_rn(__dadd_rn(lo, hi), 0.5);
+    }
+}
+
+__global__ void __launch_bounds__(MAD_THREADS)
+mad_apply_kernel(const double* __restrict__ marg, long long n, double mad_max, const MadState* __restrict__ st,
+                 double* __restrict__ bias) {
+    const double cutoff = exp(__dadd_rn(st->result[0], -__dmul_rn(mad_max, st->result[1])));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (marg[i] < cutoff) bias[i] = 0.0;
+}
+
 // ---------------------------------------------------------------------------------------
 // the fused iteration
 // ---------------------------------------------------------------------------------------
@@ -940,8 +1112,31 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
                                                                       P->min_count, do_mad, bias);
     HC_LAUNCH_CHECK();
     if (do_mad) {
-        ice_filter_mad_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(marg, nbins, P->mad_max, bias, work);
+        static const bool single = [] { const char* e = getenv("HC_ICE_MAD_SINGLE"); return e && atoi(e) != 0; }();
+        if (single) {
+            ice_filter_mad_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(marg, nbins, P->mad_max, bias, work);
+            HC_LAUNCH_CHECK();
+            return HC_OK;
+        }
+        cudaStream_t s = (cudaStream_t)stream;
+        MadState* st = nullptr;
+        HC_CUDA(cudaMallocAsync(&st, sizeof(MadState), s));
+        HC_CUDA(cudaMemsetAsync(st, 0, sizeof(MadState), s));
+        double* lg = work;
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(work + nbins);
+        long long grid = (nbins + MAD_THREADS * 4 - 1) / (MAD_THREADS * 4);
+        const long long cap = 2ll * hc_num_sms();
+        if (grid > cap) grid = cap;
+        const unsigned g = (unsigned)grid;
+        mad_keys_kernel<0><<<g, MAD_THREADS, 0, s>>>(marg, nbins, lg, keys, st);
+        for (int shift = 56; shift >= 0; shift -= 8) mad_select_pass_kernel<<<g, MAD_THREADS, 0, s>>>(keys, nbins, shift, st);
+        mad_median_kernel<0><<<g, MAD_THREADS, 0, s>>>(keys, nbins, st);
+        mad_keys_kernel<1><<<g, MAD_THREADS, 0, s>>>(marg, nbins, lg, keys, st);
+        for (int shift = 56; shift >= 0; shift -= 8) mad_select_pass_kernel<<<g, MAD_THREADS, 0, s>>>(keys, nbins, shift, st);
+        mad_median_kernel<1><<<g, MAD_THREADS, 0, s>>>(keys, nbins, st);
+        mad_apply_kernel<<<g, MAD_THREADS, 0, s>>>(marg, nbins, P->mad_max, st, bias);
         HC_LAUNCH_CHECK();
+        HC_CUDA(cudaFreeAsync(st, s));
     }
     return HC_OK;
 }

@@ -6,20 +6,33 @@
 //
 // Roofline: HBM-bound, 8*P (histogram) + passes*16*P bytes for P keys.
 #include "hc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
+#ifndef HC_SORT_DEFAULT_THREADS
+#define HC_SORT_DEFAULT_THREADS 512
+#endif
+constexpr int SORT_DEFAULT_THREADS = HC_SORT_DEFAULT_THREADS;
 constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys = 32 KB
+constexpr int SORT_MIN_TILE = 256 * SORT_ITEMS;       // 4096 keys = 32 KB
 constexpr int MAX_PASSES = 8;
 #ifndef HC_SORT_MIN_BLOCKS
 #define HC_SORT_MIN_BLOCKS 4
 #endif
 constexpr int SORT_MIN_BLOCKS = HC_SORT_MIN_BLOCKS;   // 64 registers/thread -> 4 CTAs (32 warps) per SM
+
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 
 constexpr unsigned long long FLAG_AGG = 1ull << 62;
 constexpr unsigned long long FLAG_INC = 2ull << 62;
@@ -62,32 +75,38 @@ __global__ void __launch_bounds__(RADIX) radix_scan_kernel(unsigned long long* _
 }
 
 // ---- one digit pass -------------------------------------------------------------------
-struct SortSmem {
-    unsigned long long keys[SORT_TILE];
-    unsigned int warp_hist[SORT_WARPS][RADIX];
+// THREADS x 16 keys per tile.  The tile size sets the length of the digit runs a tile writes (tile / 256 keys on a
+// uniform digit): 128 B runs at 4096 keys, 256 B at 8192 -- the low-digit passes are bound by those scattered writes
+// (measured 2.1 TB/s at 4096 against 3.3 TB/s for the top digit, whose 64 occupied bins give 512 B runs).
+template <int THREADS>
+struct SortSmemT {
+    unsigned long long keys[THREADS * SORT_ITEMS];
+    unsigned int warp_hist[THREADS / 32][RADIX];
     unsigned int tile_off[RADIX];       // exclusive scan of the tile's digit totals
     unsigned long long gbase[RADIX];    // global position of the tile's first key of each digit
-    unsigned int scan_tmp[SORT_WARPS];
+    unsigned int scan_tmp[RADIX / 32];
     unsigned int tile_id;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS)
+template <int SORT_LOOKBACK, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
                       int shift, const unsigned long long* __restrict__ digit_base /*[256]*/,
                       unsigned long long* status /*[num_tiles][256]*/, unsigned int* tile_counter) {
+    constexpr int WARPS = THREADS / 32, TILE = THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
+    SortSmemT<THREADS>& sm = *reinterpret_cast<SortSmemT<THREADS>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) sm.tile_id = atomicAdd(tile_counter, 1u);   // tiles are claimed in launch order
-    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const long long tile = sm.tile_id;
-    const long long base = tile * SORT_TILE;
-    const int valid = (int)min((long long)SORT_TILE, n - base);
+    const long long base = tile * TILE;
+    const int valid = (int)min((long long)TILE, n - base);
 
     // warp-striped load keeps memory order == (warp, item, lane) order -> stable ranking
     unsigned long long key[SORT_ITEMS];
-    unsigned int rank[SORT_ITEMS];
+    unsigned int rank2[SORT_ITEMS / 2];    // ranks inside the warp's digit run (< 65536): two per register
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
@@ -108,46 +127,26 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
             sm.warp_hist[w][d] = prev + __popc(m);
         }
         prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[i] = prev + __popc(m & lt);
+        const unsigned rk = prev + __popc(m & lt);
+        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (rk << 16)) : rk;
         __syncwarp();
     }
     __syncthreads();
 
-    // per digit (thread d): exclusive scan over warps, tile total
-    unsigned total;
-    {
+    // per digit (threads 0..255): exclusive scan over warps, tile total -- published at once so that later tiles can add it
+    unsigned total = 0;
+    unsigned long long* my = status + tile * RADIX + tid;
+    if (tid < RADIX) {
         unsigned run = 0;
 #pragma unroll
-        for (int ww = 0; ww < SORT_WARPS; ++ww) {
+        for (int ww = 0; ww < WARPS; ++ww) {
             const unsigned c = sm.warp_hist[ww][tid];
             sm.warp_hist[ww][tid] = run;
             run += c;
         }
         total = run;
-    }
-    // decoupled look-back for digit `tid`
-    {
-        unsigned long long* my = status + tile * RADIX + tid;
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_INC | total;
-        } else {
-            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_AGG | total;
-            long long t = tile - 1;
-            while (true) {
-                const volatile unsigned long long* p = status + t * RADIX + tid;
-                unsigned long long v;
-                do { v = *p; } while ((v & FLAG_MASK) == 0);
-                excl += v & ~FLAG_MASK;
-                if ((v & FLAG_MASK) == FLAG_INC) break;
-                --t;
-            }
-            *reinterpret_cast<volatile unsigned long long*>(my) = FLAG_INC | (excl + total);
-        }
-        sm.gbase[tid] = digit_base[tid] + excl;
-    }
-    // block exclusive scan of the digit totals -> position of each digit run inside the tile
-    {
+        st_relaxed_u64(my, (tile == 0 ? FLAG_INC : FLAG_AGG) | total);
+        // block exclusive scan of the digit totals -> position of each digit run inside the tile
         unsigned incl = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -155,24 +154,58 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
             if (lane >= o) incl += y;
         }
         if (lane == 31) sm.scan_tmp[w] = incl;
-        __syncthreads();
+        total = incl - total;      // exclusive inside the warp, for the moment
+    }
+    __syncthreads();
+    if (tid < RADIX) {
         unsigned woff = 0;
         for (int ww = 0; ww < w; ++ww) woff += sm.scan_tmp[ww];
-        sm.tile_off[tid] = woff + incl - total;
+        sm.tile_off[tid] = woff + total;
     }
     __syncthreads();
 
-    // reorder inside shared memory so the global writes are contiguous per digit run
+    // reorder inside shared memory so the global writes are contiguous per digit run (the keys leave the registers
+    // before the look-back needs them for its window)
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
         if (j < valid) {
             const unsigned d = (unsigned)((key[i] >> shift) & (RADIX - 1));
-            sm.keys[sm.tile_off[d] + sm.warp_hist[w][d] + rank[i]] = key[i];
+            sm.keys[sm.tile_off[d] + sm.warp_hist[w][d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu)] = key[i];
         }
     }
+
+    // decoupled look-back for digit `tid`: SORT_LOOKBACK status words are fetched at once and consumed in order (a walk of
+    // one L2 round trip per predecessor is ~20 hops long at this tile rate)
+    if (tid < RADIX) {
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            // the tile total again: next digit's offset minus this one's (the last digit: up to `valid`)
+            const unsigned mine = (tid == RADIX - 1 ? (unsigned)valid : sm.tile_off[tid + 1]) - sm.tile_off[tid];
+            long long t = tile - 1;
+            bool found = false;
+            while (!found) {
+                unsigned long long v[SORT_LOOKBACK];
+#pragma unroll
+                for (int u = 0; u < SORT_LOOKBACK; ++u)
+                    v[u] = (t - u >= 0) ? ld_relaxed_u64(status + (t - u) * RADIX + tid) : FLAG_INC;   // before tile 0: nothing
+#pragma unroll
+                for (int u = 0; u < SORT_LOOKBACK; ++u) {
+                    if (!found) {
+                        unsigned long long x = v[u];
+                        while ((x & FLAG_MASK) == 0) x = ld_relaxed_u64(status + (t - u) * RADIX + tid);   // not published yet
+                        excl += x & ~FLAG_MASK;
+                        found = (x & FLAG_MASK) == FLAG_INC;
+                    }
+                }
+                t -= SORT_LOOKBACK;
+            }
+            st_relaxed_u64(my, FLAG_INC | (excl + mine));
+        }
+        sm.gbase[tid] = digit_base[tid] + excl;
+    }
     __syncthreads();
-    for (int j = tid; j < valid; j += SORT_THREADS) {
+    for (int j = tid; j < valid; j += THREADS) {
         const unsigned long long k = sm.keys[j];
         const unsigned d = (unsigned)((k >> shift) & (RADIX - 1));
         out[sm.gbase[d] + (unsigned)(j - sm.tile_off[d])] = k;
@@ -181,9 +214,10 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
 
 }  // namespace
 
-// Workspace layout (bytes): [passes*256 u64 histogram][num_tiles*256 u64 status][16 B counters]
+// Workspace layout (bytes): [passes*256 u64 histogram][16 B counters][num_tiles*256 u64 status]; sized for the
+// smallest tile (4096 keys)
 extern "C" int64_t hc_sort_work_bytes(int64_t n) {
-    const int64_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int64_t tiles = (n + SORT_MIN_TILE - 1) / SORT_MIN_TILE;
     return (int64_t)sizeof(unsigned long long) * (MAX_PASSES * RADIX + (tiles > 0 ? tiles : 1) * RADIX) + 64;
 }
 
@@ -198,10 +232,9 @@ extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tm
     if (n <= 1 || passes == 0) return HC_OK;
     HC_REQUIRE(passes <= MAX_PASSES, "too many digit passes");
     cudaStream_t s = (cudaStream_t)stream;
-    const long long tiles = (n + SORT_TILE - 1) / SORT_TILE;
     unsigned long long* ghist = reinterpret_cast<unsigned long long*>(work);
-    unsigned long long* status = ghist + MAX_PASSES * RADIX;
-    unsigned int* counter = reinterpret_cast<unsigned int*>(status + tiles * RADIX);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ghist + MAX_PASSES * RADIX);
+    unsigned long long* status = ghist + MAX_PASSES * RADIX + 2;
 
     HC_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * MAX_PASSES * RADIX, s));
     {
@@ -216,13 +249,28 @@ extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tm
     radix_scan_kernel<<<passes, RADIX, 0, s>>>(ghist);
     HC_LAUNCH_CHECK();
 
-    const size_t smem = sizeof(SortSmem);
-    HC_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // variants: status words fetched per look-back step (HC_SORT_LOOKBACK = 1, 2, 4, 8) and threads per tile
+    // (HC_SORT_THREADS = 256, 512, 1024 -> 4096 / 8192 / 16384 keys per tile)
+    static const int lookback = [] { const char* e = getenv("HC_SORT_LOOKBACK"); const int v = e ? atoi(e) : 8;
+                                     return (v == 1 || v == 2 || v == 4) ? v : 8; }();
+    static const int threads = [] { const char* e = getenv("HC_SORT_THREADS"); const int v = e ? atoi(e) : SORT_DEFAULT_THREADS;
+                                    return (v == 256 || v == 512 || v == 1024) ? v : SORT_DEFAULT_THREADS; }();
+    using Kern = void (*)(const unsigned long long*, unsigned long long*, long long, int, const unsigned long long*,
+                          unsigned long long*, unsigned int*);
+    static const Kern table[3][4] = {
+        {radix_onesweep_kernel<1, 256, 4>, radix_onesweep_kernel<2, 256, 4>, radix_onesweep_kernel<4, 256, 4>, radix_onesweep_kernel<8, 256, 4>},
+        {radix_onesweep_kernel<1, 512, 2>, radix_onesweep_kernel<2, 512, 2>, radix_onesweep_kernel<4, 512, 2>, radix_onesweep_kernel<8, 512, 2>},
+        {radix_onesweep_kernel<1, 1024, 1>, radix_onesweep_kernel<2, 1024, 1>, radix_onesweep_kernel<4, 1024, 1>, radix_onesweep_kernel<8, 1024, 1>}};
+    const Kern kern = table[threads == 256 ? 0 : threads == 512 ? 1 : 2][lookback == 1 ? 0 : lookback == 2 ? 1 : lookback == 4 ? 2 : 3];
+    const size_t smem = threads == 256 ? sizeof(SortSmemT<256>) : threads == 512 ? sizeof(SortSmemT<512>) : sizeof(SortSmemT<1024>);
+    const long long tile_keys = (long long)threads * SORT_ITEMS;
+    const long long tiles = (n + tile_keys - 1) / tile_keys;
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long* src = keys;
     unsigned long long* dst = tmp;
     for (int p = 0; p < passes; ++p) {
-        HC_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned long long) * tiles * RADIX + 16, s));
-        radix_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, smem, s>>>(
+        HC_CUDA(cudaMemsetAsync(counter, 0, 16 + sizeof(unsigned long long) * tiles * RADIX, s));
+        kern<<<(unsigned)tiles, threads, smem, s>>>(
             src, dst, n, begin_bit + RADIX_BITS * p, ghist + p * RADIX, status, counter);
         HC_LAUNCH_CHECK();
         unsigned long long* t = src; src = dst; dst = t;
