@@ -88,7 +88,23 @@ struct SortSmemT {
     unsigned int tile_id;
 };
 
-template <int SORT_LOOKBACK, int THREADS, int MINB>
+// Lanes of the warp that hold the same 8-bit digit.  MATCH.ANY does it in one instruction, but it runs on the address
+// divergence unit at about one warp instruction per 60 cycles and SM: with 16 of them per thread the pass sat at 81 % ADU
+// utilisation and 2.1 TB/s (profiles/r2r_ncu_onesweep_v2.json).  Eight ballots (ALU pipe) narrow the mask bit by bit.
+template <bool BALLOT>
+__device__ __forceinline__ unsigned match_digit(unsigned d, bool ok) {
+    if (!BALLOT) return __match_any_sync(0xffffffffu, ok ? d : (unsigned)(RADIX + (threadIdx.x & 31)));   // padding lanes match nobody
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
+template <int SORT_LOOKBACK, int THREADS, int MINB, bool BALLOT>
 __global__ void __launch_bounds__(THREADS, MINB)
 radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
                       int shift, const unsigned long long* __restrict__ digit_base /*[256]*/,
@@ -117,9 +133,8 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
         const bool ok = j < valid;
-        // padding lanes get a private pseudo-digit so they match nobody and count nowhere
-        const unsigned d = ok ? (unsigned)((key[i] >> shift) & (RADIX - 1)) : (unsigned)(RADIX + lane);
-        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const unsigned d = (unsigned)((key[i] >> shift) & (RADIX - 1));
+        const unsigned m = match_digit<BALLOT>(d, ok);          // padding lanes match nobody and count nowhere
         const int leader = __ffs(m) - 1;
         unsigned prev = 0;
         if (ok && lane == leader) {
@@ -249,20 +264,21 @@ extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tm
     radix_scan_kernel<<<passes, RADIX, 0, s>>>(ghist);
     HC_LAUNCH_CHECK();
 
-    // variants: status words fetched per look-back step (HC_SORT_LOOKBACK = 1, 2, 4, 8) and threads per tile
-    // (HC_SORT_THREADS = 256, 512, 1024 -> 4096 / 8192 / 16384 keys per tile)
-    static const int lookback = [] { const char* e = getenv("HC_SORT_LOOKBACK"); const int v = e ? atoi(e) : 8;
-                                     return (v == 1 || v == 2 || v == 4) ? v : 8; }();
+    // variants: HC_SORT_LOOKBACK = 1 | 8 status words fetched per look-back step; HC_SORT_THREADS = 256 | 512 threads per tile
+    // (4096 / 8192 keys); HC_SORT_MATCH = any | ballot
+    static const int lookback = [] { const char* e = getenv("HC_SORT_LOOKBACK"); return (e && atoi(e) == 1) ? 1 : 8; }();
     static const int threads = [] { const char* e = getenv("HC_SORT_THREADS"); const int v = e ? atoi(e) : SORT_DEFAULT_THREADS;
-                                    return (v == 256 || v == 512 || v == 1024) ? v : SORT_DEFAULT_THREADS; }();
+                                    return (v == 256 || v == 512) ? v : SORT_DEFAULT_THREADS; }();
+    static const bool ballot = [] { const char* e = getenv("HC_SORT_MATCH"); return !(e && e[0] == 'a'); }();
     using Kern = void (*)(const unsigned long long*, unsigned long long*, long long, int, const unsigned long long*,
                           unsigned long long*, unsigned int*);
-    static const Kern table[3][4] = {
-        {radix_onesweep_kernel<1, 256, 4>, radix_onesweep_kernel<2, 256, 4>, radix_onesweep_kernel<4, 256, 4>, radix_onesweep_kernel<8, 256, 4>},
-        {radix_onesweep_kernel<1, 512, 2>, radix_onesweep_kernel<2, 512, 2>, radix_onesweep_kernel<4, 512, 2>, radix_onesweep_kernel<8, 512, 2>},
-        {radix_onesweep_kernel<1, 1024, 1>, radix_onesweep_kernel<2, 1024, 1>, radix_onesweep_kernel<4, 1024, 1>, radix_onesweep_kernel<8, 1024, 1>}};
-    const Kern kern = table[threads == 256 ? 0 : threads == 512 ? 1 : 2][lookback == 1 ? 0 : lookback == 2 ? 1 : lookback == 4 ? 2 : 3];
-    const size_t smem = threads == 256 ? sizeof(SortSmemT<256>) : threads == 512 ? sizeof(SortSmemT<512>) : sizeof(SortSmemT<1024>);
+    static const Kern table[2][2][2] = {
+        {{radix_onesweep_kernel<1, 256, 4, false>, radix_onesweep_kernel<1, 256, 4, true>},
+         {radix_onesweep_kernel<8, 256, 4, false>, radix_onesweep_kernel<8, 256, 4, true>}},
+        {{radix_onesweep_kernel<1, 512, 2, false>, radix_onesweep_kernel<1, 512, 2, true>},
+         {radix_onesweep_kernel<8, 512, 2, false>, radix_onesweep_kernel<8, 512, 2, true>}}};
+    const Kern kern = table[threads == 256 ? 0 : 1][lookback == 1 ? 0 : 1][ballot ? 1 : 0];
+    const size_t smem = threads == 256 ? sizeof(SortSmemT<256>) : sizeof(SortSmemT<512>);
     const long long tile_keys = (long long)threads * SORT_ITEMS;
     const long long tiles = (n + tile_keys - 1) / tile_keys;
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -15,6 +15,8 @@
 // Roofline: HBM-bound, (4+4+4+4+8) N^2 = 24 N^2 bytes per haplotype matrix (+4 N^2 for TM).
 #include <math.h>
 #include "hc_common.cuh"
+#include <string.h>
+#include <vector>
 #include "hc_select.cuh"
 
 namespace {
@@ -221,7 +223,8 @@ __device__ __forceinline__ void load_tile_fast(const int32_t* __restrict__ X, in
 // loads per cell: 31 thread instructions per cell, issue-bound at 2.6 TB/s -- profiles/r1d_ncu_secondary_raw.csv.)
 template <int PASS, bool GAP>
 __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, int r0, int c0, const int32_t* sA, const int32_t* tB,
-                                              int ldb, const double* vr, const double* vc, double* sV, double (*colred)[T], double* red) {
+                                              int ldb, const double* vr, const double* vc, double* sV, double (*colred)[T], double* red,
+                                              int cta) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps; a warp covers one tile row at a time
     // per-column values of this thread's two columns
     double raj[2], rsj[2];
@@ -277,7 +280,7 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
         }
     } else if (PASS == PASS_TOTAL) {
         const double s = block_sum(tot, red);
-        if (threadIdx.x == 0) a.cta_partial[blockIdx.x] = (I != J) ? 2.0 * s : s;
+        if (threadIdx.x == 0) a.cta_partial[cta] = (I != J) ? 2.0 * s : s;
     } else {
         const double rf = a.scalars[0];
 #pragma unroll
@@ -306,8 +309,9 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
     }
 }
 
+// one tile pair (`cta` = its index in the row-major enumeration of the upper triangle) of one matrix
 template <int PASS>
-__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
+__device__ __forceinline__ void sym_pass_run(SymArgs a, int cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* sA = reinterpret_cast<int32_t*>(smem_raw);     // [T][T]    tile (I,J)
     int32_t* sB = sA + T * T;                               // [T][LDB]  tile (J,I)
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
 
     if (a.ngap_dev) a.has_gap = *a.ngap_dev > 0;
     int I, J;
-    tile_index(blockIdx.x, a.nT, &I, &J);
+    tile_index(cta, a.nT, &I, &J);
     const int r0 = I * T, c0 = J * T;
     const bool inside = r0 + T <= a.n && c0 + T <= a.n && c0 + T <= (int)a.ld && r0 + T <= (int)a.ld;
     if (inside) {
@@ -339,18 +343,45 @@ __global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) {
     __syncthreads();
     const int32_t* tB = (I != J) ? sB : sA;
     const int ldb = (I != J) ? LDB : T;
-    if (a.has_gap) sym_pass_body<PASS, true>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red);
-    else sym_pass_body<PASS, false>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red);
+    if (a.has_gap) sym_pass_body<PASS, true>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red, cta);
+    else sym_pass_body<PASS, false>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red, cta);
 }
 
-__global__ void __launch_bounds__(256) recip_alpha_kernel(SymArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+template <int PASS>
+__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) { sym_pass_run<PASS>(a, (int)blockIdx.x); }
+
+// ---- all matrices of a batch in one launch per pass -------------------------------------------
+// (46 matrices x 6 dependent launches, most of them small, cost 1.1 ms of launch-latency chains out of 5.8 ms --
+// profiles/r2s_c3_launches.csv; the matrices are independent, so every pass runs over the tile pairs of all of them.)
+struct SymBatch {
+    const SymArgs* mats;          // device array, one entry per matrix
+    const int* pair_off;          // [nmat+1] prefix of the tile-pair counts
+    const int64_t* const* rowsum; // [nmat] row sums of the input matrix (for the rescale factor)
+    int nmat;
+};
+
+__device__ __forceinline__ int batch_find(const int* __restrict__ off, int nmat, int x) {
+    int lo = 0, hi = nmat;        // largest k with off[k] <= x
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= x) lo = mid; else hi = mid; }
+    return lo;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(TS_THREADS) sym_pass_batch_kernel(SymBatch b) {
+    const int k = batch_find(b.pair_off, b.nmat, (int)blockIdx.x);
+    sym_pass_run<PASS>(b.mats[k], (int)blockIdx.x - b.pair_off[k]);
+}
+
+__device__ __forceinline__ void recip_alpha_run(const SymArgs& a, int i) {
     if (i < a.nT * T) a.ra[i] = i < a.n ? 1.0 / a.alpha[i] : 0.0;
+}
+__global__ void __launch_bounds__(256) recip_alpha_kernel(SymArgs a) { recip_alpha_run(a, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(256) recip_alpha_batch_kernel(SymBatch b) {        // grid.y = matrix
+    recip_alpha_run(b.mats[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // s_i = (sum_K partial[K][i])^(2/3), zeros -> 1; store the reciprocal
-__global__ void __launch_bounds__(256) vc_scale_kernel(SymArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void vc_scale_run(const SymArgs& a, int i) {
     const int64_t np = (int64_t)a.nT * T;
     if (i >= np) return;
     double s = 0.0;
@@ -359,11 +390,12 @@ __global__ void __launch_bounds__(256) vc_scale_kernel(SymArgs a) {
     if (s == 0.0) s = 1.0;
     a.rs[i] = 1.0 / s;
 }
+__global__ void __launch_bounds__(256) vc_scale_kernel(SymArgs a) { vc_scale_run(a, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(256) vc_scale_batch_kernel(SymBatch b) { vc_scale_run(b.mats[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
 
 // RF = mean(X) / mean(Cor)
-__global__ void __launch_bounds__(1024)
-vc_rescale_factor_kernel(const double* __restrict__ cta_partial, int npairs, const int64_t* __restrict__ rowsum_x,
-                         int n, double* __restrict__ scalars) {
+__device__ __forceinline__ void vc_rescale_factor_run(const double* __restrict__ cta_partial, int npairs,
+                                                      const int64_t* __restrict__ rowsum_x, int n, double* __restrict__ scalars) {
     __shared__ double red[32];
     __shared__ long long redll[32];
     double t = 0.0;
@@ -379,6 +411,16 @@ vc_rescale_factor_kernel(const double* __restrict__ cta_partial, int npairs, con
         scalars[1] = mean_x;
         scalars[2] = mean_cor;
     }
+}
+__global__ void __launch_bounds__(1024)
+vc_rescale_factor_kernel(const double* __restrict__ cta_partial, int npairs, const int64_t* __restrict__ rowsum_x,
+                         int n, double* __restrict__ scalars) {
+    vc_rescale_factor_run(cta_partial, npairs, rowsum_x, n, scalars);
+}
+__global__ void __launch_bounds__(1024) vc_rescale_factor_batch_kernel(SymBatch b) {      // one CTA per matrix
+    const SymArgs& a = b.mats[blockIdx.x];
+    vc_rescale_factor_run(a.cta_partial, b.pair_off[blockIdx.x + 1] - b.pair_off[blockIdx.x], b.rowsum[blockIdx.x], a.n,
+                          const_cast<double*>(a.scalars));
 }
 
 // row sums + non-zero counts of every matrix of a batch (one warp per global row)
@@ -537,28 +579,69 @@ extern "C" int hc_twostep_batch(const int32_t* tmats, const int64_t* t_off, cons
     twostep_alpha_kernel<<<nchrom, 1024, 0, s>>>(a);
     HC_LAUNCH_CHECK();
 
-    const size_t smem_tiles = (size_t)(T * T + T * LDB) * sizeof(int32_t);
-    const size_t smem_write = smem_tiles + (size_t)T * LDB * sizeof(double);
-    HC_CUDA(cudaFuncSetAttribute(sym_pass_kernel<PASS_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+    // per-matrix descriptors and scratch (stream-ordered allocation, released before returning); every pass is ONE launch
+    // over the tile pairs of all matrices
+    std::vector<SymArgs> mats;
+    std::vector<int> pair_off(1, 0);
+    std::vector<const int64_t*> rowsum;
+    int64_t scratch_bytes = 0;
+    int max_np = 0;
+    for (int k = 0; k < 2 * nchrom; ++k) {
+        const int c = k % nchrom, n = h_sizes[c];
+        if (n == 0) continue;
+        scratch_bytes += (hc_twostep_work_bytes(n) + 255) & ~(int64_t)255;
+    }
+    const size_t desc_bytes = ((sizeof(SymArgs) + sizeof(int) + sizeof(void*)) * (size_t)(2 * nchrom + 1) + 255) & ~(size_t)255;
+    unsigned char* scratch = nullptr;
+    HC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)scratch_bytes + desc_bytes + 256, s));
+    unsigned char* cur = scratch + desc_bytes;
     for (int k = 0; k < 2 * nchrom; ++k) {
         const int c = k % nchrom, hap = k / nchrom, n = h_sizes[c];
         if (n == 0) continue;
         const int nT = (n + T - 1) / T;
-        const int npairs = nT * (nT + 1) / 2;
-        TwoStepWork w = carve(mwork, n);
+        const int64_t npairs64 = (int64_t)nT * (nT + 1) / 2;
+        if ((int64_t)pair_off.back() + npairs64 >= (1ll << 31)) { cudaFreeAsync(scratch, s); HC_REQUIRE(false, "batch too large"); }
+        TwoStepWork w = carve(cur, n);
+        cur += (hc_twostep_work_bytes(n) + 255) & ~(int64_t)255;
         SymArgs g;
         g.X = hmats + h_hoff[k]; g.ld = h_hld[k]; g.n = n; g.nT = nT;
         g.alpha = alpha + h_tbin[c]; g.gapflag = gapflag + h_hbin[k]; g.has_gap = 0; g.ngap_dev = ngap + 2 * c + hap;
         g.partial = w.partial; g.rs = w.rs; g.ra = w.ra; g.cta_partial = w.cta_partial; g.scalars = w.scalars;
         g.out = out + h_out_off[k]; g.ld_out = n;
-        recip_alpha_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(g);
-        sym_pass_kernel<PASS_ROWSUM><<<npairs, TS_THREADS, smem_tiles, s>>>(g);
-        vc_scale_kernel<<<(nT * T + 255) / 256, 256, 0, s>>>(g);
-        sym_pass_kernel<PASS_TOTAL><<<npairs, TS_THREADS, smem_tiles, s>>>(g);
-        vc_rescale_factor_kernel<<<1, 1024, 0, s>>>(w.cta_partial, npairs, rs_h + h_hbin[k], n, w.scalars);
-        sym_pass_kernel<PASS_WRITE><<<npairs, TS_THREADS, smem_write, s>>>(g);
+        mats.push_back(g);
+        pair_off.push_back(pair_off.back() + (int)npairs64);
+        rowsum.push_back(rs_h + h_hbin[k]);
+        max_np = nT * T > max_np ? nT * T : max_np;
+    }
+    const int nmat = (int)mats.size();
+    if (nmat > 0) {
+        // descriptors: [SymArgs x nmat][rowsum pointers x nmat][pair_off x (nmat+1)], one staged upload
+        std::vector<unsigned char> stage(desc_bytes, 0);
+        size_t o_rows = sizeof(SymArgs) * (size_t)nmat;
+        size_t o_pair = o_rows + sizeof(void*) * (size_t)nmat;
+        memcpy(stage.data(), mats.data(), sizeof(SymArgs) * (size_t)nmat);
+        memcpy(stage.data() + o_rows, rowsum.data(), sizeof(void*) * (size_t)nmat);
+        memcpy(stage.data() + o_pair, pair_off.data(), sizeof(int) * (size_t)(nmat + 1));
+        HC_CUDA(cudaMemcpyAsync(scratch, stage.data(), desc_bytes, cudaMemcpyHostToDevice, s));   // pageable source: staged before return
+        SymBatch b;
+        b.mats = reinterpret_cast<const SymArgs*>(scratch);
+        b.rowsum = reinterpret_cast<const int64_t* const*>(scratch + o_rows);
+        b.pair_off = reinterpret_cast<const int*>(scratch + o_pair);
+        b.nmat = nmat;
+        const size_t smem_tiles = (size_t)(T * T + T * LDB) * sizeof(int32_t);
+        const size_t smem_write = smem_tiles + (size_t)T * LDB * sizeof(double);
+        HC_CUDA(cudaFuncSetAttribute(sym_pass_batch_kernel<PASS_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+        const dim3 vgrid((unsigned)((max_np + 255) / 256), (unsigned)nmat);
+        const unsigned total_pairs = (unsigned)pair_off.back();
+        recip_alpha_batch_kernel<<<vgrid, 256, 0, s>>>(b);
+        sym_pass_batch_kernel<PASS_ROWSUM><<<total_pairs, TS_THREADS, smem_tiles, s>>>(b);
+        vc_scale_batch_kernel<<<vgrid, 256, 0, s>>>(b);
+        sym_pass_batch_kernel<PASS_TOTAL><<<total_pairs, TS_THREADS, smem_tiles, s>>>(b);
+        vc_rescale_factor_batch_kernel<<<(unsigned)nmat, 1024, 0, s>>>(b);
+        sym_pass_batch_kernel<PASS_WRITE><<<total_pairs, TS_THREADS, smem_write, s>>>(b);
         hc_count_launch(6);
     }
+    HC_CUDA(cudaFreeAsync(scratch, s));
     HC_CUDA(cudaGetLastError());
     return HC_OK;
 }
