@@ -288,6 +288,105 @@ ent_heads_kernel(const unsigned long long* __restrict__ ent, const unsigned long
     }
 }
 
+// ---- heads in ONE pass: flags, tile counts and their prefix (decoupled look-back over one status word per tile) ----------
+// Replaces ent_count_kernel + the single-CTA scan + ent_heads_kernel (1.9 + 0.3 + 3.9 ms at 1 G entries) for the default path:
+// upos[u] = position of the u-th head, *total = number of heads.
+constexpr int HS_THREADS = 256;
+constexpr int HS_ITEMS = 16;
+constexpr int HS_TILE = HS_THREADS * HS_ITEMS;
+constexpr unsigned long long HS_AGG = 1ull << 62, HS_INC = 2ull << 62, HS_MASK = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long hs_ld(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void hs_st(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(HS_THREADS)
+ent_heads_scan_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_valid_p, int cnt_bits,
+                      unsigned long long* status /*[tiles]*/, unsigned int* tile_counter, int64_t* __restrict__ upos,
+                      int64_t* __restrict__ total) {
+    __shared__ unsigned int tile_s;
+    __shared__ int wtot[HS_THREADS / 32];
+    __shared__ long long excl_s;
+    if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);      // tiles are claimed in launch order
+    __syncthreads();
+    const long long tile = tile_s;
+    const long long m = (long long)*n_valid_p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // a warp owns 16 x 32 consecutive entries; item k of a lane is entry wbase + 32 k + lane (coalesced loads and stores)
+    const long long wbase = tile * HS_TILE + (long long)wid * (32 * HS_ITEMS);
+    unsigned long long c[HS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < HS_ITEMS; ++k) {
+        const long long i = wbase + 32 * k + lane;
+        c[k] = i < m ? ent[i] >> cnt_bits : 0ull;
+    }
+    unsigned long long carry = (lane == 0 && wbase > 0 && wbase < m) ? ent[wbase - 1] >> cnt_bits : 0ull;   // cell before (k, lane 0)
+    unsigned bal[HS_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < HS_ITEMS; ++k) {
+        const long long i = wbase + 32 * k + lane;
+        unsigned long long prev = __shfl_up_sync(0xffffffffu, c[k], 1);
+        if (lane == 0) prev = carry;
+        bal[k] = __ballot_sync(0xffffffffu, i < m && (i == 0 || c[k] != prev));
+        carry = __shfl_sync(0xffffffffu, c[k], 31);
+        cnt += __popc(bal[k]);                                      // warp-uniform
+    }
+    if (lane == 0) wtot[wid] = cnt;
+    __syncthreads();
+    int woff = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < HS_THREADS / 32; ++w) { if (w < wid) woff += wtot[w]; tile_total += wtot[w]; }
+    // warp 0: publish, then look back 32 tiles at a time
+    if (wid == 0) {
+        long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) hs_st(status, HS_INC | (unsigned long long)tile_total);
+        } else {
+            if (lane == 0) hs_st(status + tile, HS_AGG | (unsigned long long)tile_total);
+            long long t = tile - 1;
+            while (true) {
+                const long long src = t - lane;
+                unsigned long long v = src >= 0 ? hs_ld(status + src) : HS_INC;       // before tile 0: inclusive zero
+                // every lane up to the first inclusive one must be published
+                while (true) {
+                    const unsigned inc = __ballot_sync(0xffffffffu, (v & HS_MASK) == HS_INC);
+                    const unsigned need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;   // lanes 0 .. first inclusive
+                    const unsigned unpub = __ballot_sync(0xffffffffu, (v & HS_MASK) == 0) & need;
+                    if (!unpub) break;
+                    if ((unpub >> lane) & 1u) v = hs_ld(status + src);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (v & HS_MASK) == HS_INC);
+                const unsigned need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;
+                long long part = ((need >> lane) & 1u) ? (long long)(v & ~HS_MASK) : 0ll;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
+                if (inc) break;
+                t -= 32;
+            }
+            if (lane == 0) hs_st(status + tile, HS_INC | (unsigned long long)(excl + tile_total));
+        }
+        if (lane == 0) {
+            excl_s = excl;
+            if ((tile + 1) * HS_TILE >= m || tile == (long long)gridDim.x - 1) *total = excl + tile_total;   // the last tile with entries
+        }
+    }
+    __syncthreads();
+    long long o = excl_s + woff;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < HS_ITEMS; ++k) {
+        if ((bal[k] >> lane) & 1u) upos[o + __popc(bal[k] & lt)] = wbase + 32 * k + lane;
+        o += __popc(bal[k]);
+    }
+}
+
 // one reduced entry per run.  unit != 0: every input count is 1, so the run length is the count; otherwise the
 // counts of the run are added (runs are then short: at most one entry per contributing rank).
 __global__ void __launch_bounds__(256)
@@ -496,6 +595,49 @@ extern "C" int hc_entries_count(const unsigned long long* sorted, int64_t n, con
     csr_exclusive_scan_kernel<<<1, 1024, 0, s>>>(tile_heads, tiles);
     HC_LAUNCH_CHECK();
     HC_CUDA(cudaMemcpyAsync(h_nuniq, tile_heads + tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return HC_OK;
+}
+
+extern "C" int64_t hc_entries_heads_work_bytes(int64_t n) {
+    const int64_t tiles = (n + HS_TILE - 1) / HS_TILE;
+    return (int64_t)sizeof(unsigned long long) * (tiles + 4);
+}
+
+// One pass over the sorted entries: upos[u] = position of the first entry of the u-th distinct cell among the first
+// *n_valid entries (upos: up to n int64), *h_nuniq = their number (synchronises).  work: hc_entries_heads_work_bytes(n).
+extern "C" int hc_entries_heads(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
+                                int32_t cnt_bits, void* work, int64_t* upos, int64_t* h_nuniq, void* stream) {
+    HC_REQUIRE(n >= 0 && h_nuniq != nullptr && cnt_bits > 0 && cnt_bits < 64, "n>=0, h_nuniq, cnt_bits");
+    HC_REQUIRE((reinterpret_cast<uintptr_t>(sorted) & 15) == 0, "entries must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    *h_nuniq = 0;
+    const long long tiles = (n + HS_TILE - 1) / HS_TILE;
+    if (tiles == 0) return HC_OK;
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(work);
+    int64_t* total = reinterpret_cast<int64_t*>(w);                      // [0] total, [1] tile counter, [2..] status
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w + 1);
+    unsigned long long* status = w + 2;
+    HC_CUDA(cudaMemsetAsync(w, 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s));
+    ent_heads_scan_kernel<<<(unsigned)tiles, HS_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, status, counter, upos, total);
+    HC_LAUNCH_CHECK();
+    HC_CUDA(cudaMemcpyAsync(h_nuniq, total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return HC_OK;
+}
+
+// out[nuniq] from the head positions of hc_entries_heads (see hc_entries_reduce for unit / overflow).
+extern "C" int hc_entries_reduce_at(const unsigned long long* sorted, const unsigned long long* n_valid, const int64_t* upos,
+                                    int64_t nuniq, int32_t cnt_bits, int32_t unit, unsigned long long* out,
+                                    int32_t* d_overflow, int32_t* h_overflow, void* stream) {
+    HC_REQUIRE(nuniq >= 0 && d_overflow != nullptr && h_overflow != nullptr, "sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    *h_overflow = 0;
+    if (nuniq == 0) return HC_OK;
+    HC_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
+    ent_reduce_kernel<<<(unsigned)((nuniq + 255) / 256), 256, 0, s>>>(sorted, upos, nuniq, n_valid, cnt_bits, unit, out, d_overflow);
+    HC_LAUNCH_CHECK();
+    HC_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     HC_CUDA(cudaStreamSynchronize(s));
     return HC_OK;
 }

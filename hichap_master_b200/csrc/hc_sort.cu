@@ -83,7 +83,7 @@ struct SortSmemT {
     unsigned long long keys[THREADS * SORT_ITEMS];
     unsigned int warp_hist[THREADS / 32][RADIX];
     unsigned int tile_off[RADIX];       // exclusive scan of the tile's digit totals
-    unsigned long long gbase[RADIX];    // global position of the tile's first key of each digit
+    unsigned long long gbase[RADIX];    // global position of the tile's first key of each digit, minus tile_off
     unsigned int scan_tmp[RADIX / 32];
     unsigned int tile_id;
 };
@@ -128,6 +128,8 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
         const int j = w * (32 * SORT_ITEMS) + i * 32 + lane;
         key[i] = j < valid ? in[base + j] : ~0ull;
     }
+    // Ranking: lanes holding the same digit are counted by their first lane in the warp's counter row.  (Two independent
+    // half-chunk chains per warp, each with its own counter row, were measured slower: 18.7 vs 17.1 ms for 500 M keys.)
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -141,7 +143,7 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
             prev = sm.warp_hist[w][d];
             sm.warp_hist[w][d] = prev + __popc(m);
         }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
+        prev = __shfl_sync(0xffffffffu, prev, leader & 31);
         const unsigned rk = prev + __popc(m & lt);
         rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (rk << 16)) : rk;
         __syncwarp();
@@ -217,13 +219,13 @@ radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long l
             }
             st_relaxed_u64(my, FLAG_INC | (excl + mine));
         }
-        sm.gbase[tid] = digit_base[tid] + excl;
+        sm.gbase[tid] = digit_base[tid] + excl - sm.tile_off[tid];
     }
     __syncthreads();
     for (int j = tid; j < valid; j += THREADS) {
         const unsigned long long k = sm.keys[j];
         const unsigned d = (unsigned)((k >> shift) & (RADIX - 1));
-        out[sm.gbase[d] + (unsigned)(j - sm.tile_off[d])] = k;
+        out[sm.gbase[d] + (unsigned)j] = k;
     }
 }
 

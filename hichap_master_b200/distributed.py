@@ -138,7 +138,7 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     up, sent, free = lists
     cb, cnt_bits = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
     nuniq = int(up.numel())
-    tmp = free[nuniq:] if (free is not None and free.numel() >= 2 * nuniq) else None
+    tmp = free if (free is not None and free.numel() >= nuniq) else None
     slo, n_lo = kernels.transpose_entries(up, nbins, lo=sent, tmp=tmp)
     lo = slo[:int(n_lo.item())]
     inbox, cuts = exchange_entry_lists(up, lo, nbins)

@@ -407,22 +407,33 @@ class CountFieldOverflow(OverflowError):
 
 
 def reduce_entries(sorted_ent, n_valid, nbins: int, unit: bool, scratch=None):
-    """Reduce-by-cell over sorted entries -> reduced entries [nuniq].  ``scratch``: optional int64 tensor that
-    receives the result (and, behind it, the head positions) when it is large enough."""
+    """Reduce-by-cell over sorted entries -> reduced entries [nuniq] (a fresh tensor).  ``scratch``: optional int64
+    tensor of >= len(sorted_ent) elements for the head positions (the free half of the sort's ping-pong pair)."""
     dev, n = sorted_ent.device, int(sorted_ent.numel())
     cnt_bits = entry_cnt_bits(nbins)
-    work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=dev)
-    nuniq = C.c_int64(0)
-    check(lib().hc_entries_count(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), C.byref(nuniq), stream_ptr()),
-          "hc_entries_count")
-    nuniq = int(nuniq.value)
-    room = int(scratch.numel()) if scratch is not None else 0
-    out = scratch[:nuniq] if room >= nuniq else torch.empty(nuniq, dtype=torch.int64, device=dev)
-    upos = scratch[nuniq:2 * nuniq] if room >= 2 * nuniq else torch.empty(max(nuniq, 1), dtype=torch.int64, device=dev)
     d_ovf = torch.zeros(1, dtype=torch.int32, device=dev)
     h_ovf = C.c_int32(0)
-    check(lib().hc_entries_reduce(ptr(sorted_ent), n, ptr(n_valid), ptr(work), nuniq, cnt_bits, int(bool(unit)), ptr(upos),
-                                  ptr(out), ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce")
+    nuniq = C.c_int64(0)
+    if sorted_ent.data_ptr() % 16 == 0:
+        # one pass: head flags, tile counts and their prefix by decoupled look-back
+        upos = scratch if (scratch is not None and scratch.numel() >= n) else torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        work = torch.empty(int(lib().hc_entries_heads_work_bytes(n)), dtype=torch.uint8, device=dev)
+        check(lib().hc_entries_heads(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), ptr(upos), C.byref(nuniq),
+                                     stream_ptr()), "hc_entries_heads")
+        nuniq = int(nuniq.value)
+        out = torch.empty(nuniq, dtype=torch.int64, device=dev)
+        check(lib().hc_entries_reduce_at(ptr(sorted_ent), ptr(n_valid), ptr(upos), nuniq, cnt_bits, int(bool(unit)), ptr(out),
+                                         ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce_at")
+    else:
+        # count, scan, emit (three passes; any alignment)
+        work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=dev)
+        check(lib().hc_entries_count(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), C.byref(nuniq), stream_ptr()),
+              "hc_entries_count")
+        nuniq = int(nuniq.value)
+        out = torch.empty(nuniq, dtype=torch.int64, device=dev)
+        upos = torch.empty(max(nuniq, 1), dtype=torch.int64, device=dev)
+        check(lib().hc_entries_reduce(ptr(sorted_ent), n, ptr(n_valid), ptr(work), nuniq, cnt_bits, int(bool(unit)), ptr(upos),
+                                      ptr(out), ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce")
     if h_ovf.value:
         raise CountFieldOverflow("a cell holds more than 2^%d - 1 pairs" % cnt_bits)
     return out
@@ -444,7 +455,7 @@ def pairs_to_upper_entries(pairs: PairColumns, res: int, start, chrom_bins, nbin
         _raise_oob(oob, "genome-wide")
     ent = ent[:pairs.n]
     sent, free = sort_entries(ent, nbins, cnt_bits, 2)
-    # the reduced list goes into the free half of the ping-pong pair, the head positions behind it when they fit
+    # the head positions go into the free half of the ping-pong pair
     up = reduce_entries(sent, n_valid, nbins, unit=True, scratch=free)
     return up, sent, free
 
@@ -517,9 +528,9 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
     except CountFieldOverflow:
         return _pairs_to_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
     nuniq = int(up.numel())
-    # `sent` (the sorted pair entries) is dead now: it holds the lower list; the ping-pong partner of the second sort
-    # is the part of `free` behind the upper list when it is long enough
-    tmp = free[nuniq:] if (free is not None and free.numel() >= 2 * nuniq) else None
+    # `sent` (the sorted pair entries) and `free` (the head positions) are dead now: they hold the lower list and the
+    # ping-pong partner of its sort
+    tmp = free if (free is not None and free.numel() >= nuniq) else None
     slo, n_lo = transpose_entries(up, nbins, lo=sent, tmp=tmp)
     row_ptr, col, cnt = entries_to_csr(up, slo, n_lo, nbins, nbins)
     return SymCsr(row_ptr, col, cnt, nbins)
