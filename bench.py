@@ -638,6 +638,9 @@ def run_c4_section(args, world, rank, dev, peak, config="C4", standalone=False):
                                        "note": "bytes the slowest rank's stream kernel reads per launch / its mean launch time"}},
         "sort_path": {"ms": out["build_ms"], "algorithmic_bytes": (40.0 + 16.0 * 5) * npairs + 12.0 * Z,
                       "formula": "(40 + 16*passes)*P + 12*Z, passes = 5 (SURVEY 8d), aggregate",
+                      "what": ("one 64-bit entry per pair (upper-triangle cell) -> 5 onesweep passes -> reduce by cell (+ the swapped list) -> "
+                               "3 passes over the unique cells on the row bits -> row-wise merge into the symmetric CSR"
+                               + ("; reduced cells exchanged between the ranks, one more sort + add-counts reduce" if world > 1 else "")),
                       "achieved": ((40.0 + 16.0 * 5) * npairs + 12.0 * Z) / (out["build_ms"] * 1e6) / world, "peak": peak,
                       "frac": ((40.0 + 16.0 * 5) * npairs + 12.0 * Z) / (out["build_ms"] * 1e6) / world / peak},
         "parity_check": parity,

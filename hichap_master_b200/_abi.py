@@ -92,9 +92,7 @@ SIGNATURES = {
     "hc_pairs_to_entries": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "hc_entries_count": (C.c_int, [_P, _I64, _P, _I32, _P, C.POINTER(_I64), _P]),
     "hc_entries_reduce": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I32, _P, _P, _P, C.POINTER(_I32), _P]),
-    "hc_entries_heads_work_bytes": (C.c_int64, [_I64]),
-    "hc_entries_heads": (C.c_int, [_P, _I64, _P, _I32, _P, _P, C.POINTER(_I64), _P]),
-    "hc_entries_reduce_at": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, C.POINTER(_I32), _P]),
+    "hc_entries_emit": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, C.POINTER(_I32), _P]),
     "hc_entries_transpose": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _P]),
     "hc_entries_csr_work_bytes": (C.c_int64, [_I64]),
     "hc_entries_to_csr": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I64, _I64, _P, _P, _P, _P, _P]),

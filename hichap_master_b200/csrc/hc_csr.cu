@@ -288,105 +288,6 @@ ent_heads_kernel(const unsigned long long* __restrict__ ent, const unsigned long
     }
 }
 
-// ---- heads in ONE pass: flags, tile counts and their prefix (decoupled look-back over one status word per tile) ----------
-// Replaces ent_count_kernel + the single-CTA scan + ent_heads_kernel (1.9 + 0.3 + 3.9 ms at 1 G entries) for the default path:
-// upos[u] = position of the u-th head, *total = number of heads.
-constexpr int HS_THREADS = 256;
-constexpr int HS_ITEMS = 16;
-constexpr int HS_TILE = HS_THREADS * HS_ITEMS;
-constexpr unsigned long long HS_AGG = 1ull << 62, HS_INC = 2ull << 62, HS_MASK = 3ull << 62;
-
-__device__ __forceinline__ unsigned long long hs_ld(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void hs_st(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(HS_THREADS)
-ent_heads_scan_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_valid_p, int cnt_bits,
-                      unsigned long long* status /*[tiles]*/, unsigned int* tile_counter, int64_t* __restrict__ upos,
-                      int64_t* __restrict__ total) {
-    __shared__ unsigned int tile_s;
-    __shared__ int wtot[HS_THREADS / 32];
-    __shared__ long long excl_s;
-    if (threadIdx.x == 0) tile_s = atomicAdd(tile_counter, 1u);      // tiles are claimed in launch order
-    __syncthreads();
-    const long long tile = tile_s;
-    const long long m = (long long)*n_valid_p;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // a warp owns 16 x 32 consecutive entries; item k of a lane is entry wbase + 32 k + lane (coalesced loads and stores)
-    const long long wbase = tile * HS_TILE + (long long)wid * (32 * HS_ITEMS);
-    unsigned long long c[HS_ITEMS];
-#pragma unroll
-    for (int k = 0; k < HS_ITEMS; ++k) {
-        const long long i = wbase + 32 * k + lane;
-        c[k] = i < m ? ent[i] >> cnt_bits : 0ull;
-    }
-    unsigned long long carry = (lane == 0 && wbase > 0 && wbase < m) ? ent[wbase - 1] >> cnt_bits : 0ull;   // cell before (k, lane 0)
-    unsigned bal[HS_ITEMS];
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < HS_ITEMS; ++k) {
-        const long long i = wbase + 32 * k + lane;
-        unsigned long long prev = __shfl_up_sync(0xffffffffu, c[k], 1);
-        if (lane == 0) prev = carry;
-        bal[k] = __ballot_sync(0xffffffffu, i < m && (i == 0 || c[k] != prev));
-        carry = __shfl_sync(0xffffffffu, c[k], 31);
-        cnt += __popc(bal[k]);                                      // warp-uniform
-    }
-    if (lane == 0) wtot[wid] = cnt;
-    __syncthreads();
-    int woff = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < HS_THREADS / 32; ++w) { if (w < wid) woff += wtot[w]; tile_total += wtot[w]; }
-    // warp 0: publish, then look back 32 tiles at a time
-    if (wid == 0) {
-        long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) hs_st(status, HS_INC | (unsigned long long)tile_total);
-        } else {
-            if (lane == 0) hs_st(status + tile, HS_AGG | (unsigned long long)tile_total);
-            long long t = tile - 1;
-            while (true) {
-                const long long src = t - lane;
-                unsigned long long v = src >= 0 ? hs_ld(status + src) : HS_INC;       // before tile 0: inclusive zero
-                // every lane up to the first inclusive one must be published
-                while (true) {
-                    const unsigned inc = __ballot_sync(0xffffffffu, (v & HS_MASK) == HS_INC);
-                    const unsigned need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;   // lanes 0 .. first inclusive
-                    const unsigned unpub = __ballot_sync(0xffffffffu, (v & HS_MASK) == 0) & need;
-                    if (!unpub) break;
-                    if ((unpub >> lane) & 1u) v = hs_ld(status + src);
-                }
-                const unsigned inc = __ballot_sync(0xffffffffu, (v & HS_MASK) == HS_INC);
-                const unsigned need = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;
-                long long part = ((need >> lane) & 1u) ? (long long)(v & ~HS_MASK) : 0ll;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                excl += part;
-                if (inc) break;
-                t -= 32;
-            }
-            if (lane == 0) hs_st(status + tile, HS_INC | (unsigned long long)(excl + tile_total));
-        }
-        if (lane == 0) {
-            excl_s = excl;
-            if ((tile + 1) * HS_TILE >= m || tile == (long long)gridDim.x - 1) *total = excl + tile_total;   // the last tile with entries
-        }
-    }
-    __syncthreads();
-    long long o = excl_s + woff;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int k = 0; k < HS_ITEMS; ++k) {
-        if ((bal[k] >> lane) & 1u) upos[o + __popc(bal[k] & lt)] = wbase + 32 * k + lane;
-        o += __popc(bal[k]);
-    }
-}
-
 // one reduced entry per run.  unit != 0: every input count is 1, so the run length is the count; otherwise the
 // counts of the run are added (runs are then short: at most one entry per contributing rank).
 __global__ void __launch_bounds__(256)
@@ -403,6 +304,101 @@ ent_reduce_kernel(const unsigned long long* __restrict__ ent, const int64_t* __r
     else { cnt = 0; for (long long p = p0; p < p1; ++p) cnt += ent[p] & mask; }
     if (cnt > mask) { atomicOr(overflow, 1); cnt = mask; }
     out[u] = (e & ~mask) | cnt;
+}
+
+// ---- reduce (+ transpose) in one pass over the sorted entries, given the scanned per-tile head counts ---------------
+// A warp owns 16 x 32 consecutive entries (item k of a lane = entry wbase + 32 k + lane: coalesced).  Head flags come from
+// ballots; a head's run ends at the next head, found in the 16 ballot masks (backward sweep) or, for the last head of the
+// warp's chunk, by a galloping + binary search in the sorted array (a hot diagonal cell holds thousands of pairs).  The
+// head writes the reduced entry -- and, when `lo` is given, the swapped one -- at tile_off + rank: no list of head
+// positions is written or read back (that list cost 3.8 GB each way, and the look-back version of the head scan sat at a
+// barrier for 60 % of its samples: profiles/r2z_ncu_heads_scan_v1.json).
+template <bool UNIT, bool LOWER>
+__global__ void __launch_bounds__(RLE_THREADS)
+ent_emit_kernel(const unsigned long long* __restrict__ ent, const unsigned long long* __restrict__ n_valid_p, int cnt_bits,
+                const int64_t* __restrict__ tile_off, unsigned long long* __restrict__ out, unsigned long long* __restrict__ lo,
+                int col_bits, unsigned long long* __restrict__ n_lo, int32_t* __restrict__ overflow) {
+    __shared__ int wtot[RLE_THREADS / 32];
+    const long long m = (long long)*n_valid_p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long wbase = (long long)blockIdx.x * RLE_TILE + (long long)wid * (32 * RLE_ITEMS);
+    const long long wend = wbase + 32 * RLE_ITEMS;
+    const unsigned long long vmask = (1ull << cnt_bits) - 1ull;
+    unsigned long long e[RLE_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RLE_ITEMS; ++k) {
+        const long long i = wbase + 32 * k + lane;
+        e[k] = i < m ? ent[i] : 0ull;
+    }
+    // the entry before the chunk and the 32 entries behind it (the run of the chunk's last head usually ends there)
+    unsigned long long carry = (lane == 0 && wbase > 0 && wbase < m) ? ent[wbase - 1] >> cnt_bits : 0ull;
+    const unsigned long long beyond = wend + lane < m ? ent[wend + lane] >> cnt_bits : ~0ull;
+    unsigned bal[RLE_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < RLE_ITEMS; ++k) {
+        const long long i = wbase + 32 * k + lane;
+        const unsigned long long c = e[k] >> cnt_bits;
+        unsigned long long prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = carry;
+        bal[k] = __ballot_sync(0xffffffffu, i < m && (i == 0 || c != prev));
+        carry = __shfl_sync(0xffffffffu, c, 31);         // after the loop: the cell of the chunk's last entry
+        cnt += __popc(bal[k]);
+    }
+    // where the run of the chunk's LAST head ends (warp-uniform): the first entry behind the chunk with another cell
+    long long chunk_run_end;
+    {
+        const unsigned differs = __ballot_sync(0xffffffffu, beyond != carry);     // entries past m count as different
+        if (wend >= m) chunk_run_end = m;
+        else if (differs) chunk_run_end = wend + (__ffs(differs) - 1);
+        else {                                             // a long run (hot diagonal cell): gallop, then bisect
+            long long known = wend + 31, q = known + 1, step = 32;
+            while (q < m && (ent[q] >> cnt_bits) == carry) { known = q; q += step; step <<= 1; }
+            long long hi = q < m ? q : m;
+            while (hi - known > 1) {
+                const long long mid = known + ((hi - known) >> 1);
+                if ((ent[mid] >> cnt_bits) == carry) known = mid; else hi = mid;
+            }
+            chunk_run_end = hi;
+        }
+    }
+    if (lane == 0) wtot[wid] = cnt;
+    __syncthreads();
+    long long o = tile_off[blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RLE_THREADS / 32; ++w) if (w < wid) o += wtot[w];
+    o += cnt;                                            // one past the warp's last head; the sweep below runs backward
+    const unsigned gt = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+    long long next_head = chunk_run_end;                 // end of a run that no later head of the chunk closes
+    long long kept = 0;
+    const unsigned long long cmask = (1ull << col_bits) - 1ull;
+#pragma unroll
+    for (int k = RLE_ITEMS - 1; k >= 0; --k) {
+        o -= __popc(bal[k]);
+        if ((bal[k] >> lane) & 1u) {
+            const long long i = wbase + 32 * k + lane;
+            const unsigned long long cell = e[k] >> cnt_bits;
+            const unsigned above = bal[k] & gt;
+            const long long end = above ? wbase + 32 * k + (__ffs(above) - 1) : next_head;
+            unsigned long long c;
+            if (UNIT) c = (unsigned long long)(end - i);
+            else { c = e[k] & vmask; for (long long q = i + 1; q < end; ++q) c += ent[q] & vmask; }
+            if (c > vmask) { atomicOr(overflow, 1); c = vmask; }
+            const long long u = o + __popc(bal[k] & ((1u << lane) - 1u));
+            out[u] = (cell << cnt_bits) | c;
+            if (LOWER) {
+                const unsigned long long r = cell >> col_bits, cc = cell & cmask;
+                const bool off = r != cc;
+                lo[u] = off ? ((((cc << col_bits) | r) << cnt_bits) | c) : PAD_KEY;
+                kept += off;
+            }
+        }
+        if (bal[k]) next_head = wbase + 32 * k + (__ffs(bal[k]) - 1);
+    }
+    if (LOWER) {
+        kept = warp_sum_ll(kept);
+        if (lane == 0 && kept) atomicAdd(n_lo, (unsigned long long)kept);
+    }
 }
 
 // swapped copy of the off-diagonal cells; a diagonal cell becomes the padding key (sorts last)
@@ -599,49 +595,6 @@ extern "C" int hc_entries_count(const unsigned long long* sorted, int64_t n, con
     return HC_OK;
 }
 
-extern "C" int64_t hc_entries_heads_work_bytes(int64_t n) {
-    const int64_t tiles = (n + HS_TILE - 1) / HS_TILE;
-    return (int64_t)sizeof(unsigned long long) * (tiles + 4);
-}
-
-// One pass over the sorted entries: upos[u] = position of the first entry of the u-th distinct cell among the first
-// *n_valid entries (upos: up to n int64), *h_nuniq = their number (synchronises).  work: hc_entries_heads_work_bytes(n).
-extern "C" int hc_entries_heads(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
-                                int32_t cnt_bits, void* work, int64_t* upos, int64_t* h_nuniq, void* stream) {
-    HC_REQUIRE(n >= 0 && h_nuniq != nullptr && cnt_bits > 0 && cnt_bits < 64, "n>=0, h_nuniq, cnt_bits");
-    HC_REQUIRE((reinterpret_cast<uintptr_t>(sorted) & 15) == 0, "entries must be 16-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    *h_nuniq = 0;
-    const long long tiles = (n + HS_TILE - 1) / HS_TILE;
-    if (tiles == 0) return HC_OK;
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(work);
-    int64_t* total = reinterpret_cast<int64_t*>(w);                      // [0] total, [1] tile counter, [2..] status
-    unsigned int* counter = reinterpret_cast<unsigned int*>(w + 1);
-    unsigned long long* status = w + 2;
-    HC_CUDA(cudaMemsetAsync(w, 0, sizeof(unsigned long long) * (size_t)(tiles + 2), s));
-    ent_heads_scan_kernel<<<(unsigned)tiles, HS_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, status, counter, upos, total);
-    HC_LAUNCH_CHECK();
-    HC_CUDA(cudaMemcpyAsync(h_nuniq, total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
-    return HC_OK;
-}
-
-// out[nuniq] from the head positions of hc_entries_heads (see hc_entries_reduce for unit / overflow).
-extern "C" int hc_entries_reduce_at(const unsigned long long* sorted, const unsigned long long* n_valid, const int64_t* upos,
-                                    int64_t nuniq, int32_t cnt_bits, int32_t unit, unsigned long long* out,
-                                    int32_t* d_overflow, int32_t* h_overflow, void* stream) {
-    HC_REQUIRE(nuniq >= 0 && d_overflow != nullptr && h_overflow != nullptr, "sizes");
-    cudaStream_t s = (cudaStream_t)stream;
-    *h_overflow = 0;
-    if (nuniq == 0) return HC_OK;
-    HC_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
-    ent_reduce_kernel<<<(unsigned)((nuniq + 255) / 256), 256, 0, s>>>(sorted, upos, nuniq, n_valid, cnt_bits, unit, out, d_overflow);
-    HC_LAUNCH_CHECK();
-    HC_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    HC_CUDA(cudaStreamSynchronize(s));
-    return HC_OK;
-}
-
 // Reduced entries out[nuniq] (count = run length when unit, else the sum of the run's counts).  upos: nuniq int64
 // scratch.  *h_overflow = 1 when a count does not fit cnt_bits (synchronises).
 extern "C" int hc_entries_reduce(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
@@ -656,6 +609,30 @@ extern "C" int hc_entries_reduce(const unsigned long long* sorted, int64_t n, co
     ent_heads_kernel<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, reinterpret_cast<const int64_t*>(work), upos);
     HC_LAUNCH_CHECK();
     ent_reduce_kernel<<<(unsigned)((nuniq + 255) / 256), 256, 0, s>>>(sorted, upos, nuniq, n_valid, cnt_bits, unit, out, d_overflow);
+    HC_LAUNCH_CHECK();
+    HC_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HC_CUDA(cudaStreamSynchronize(s));
+    return HC_OK;
+}
+
+// The reduction in one pass after hc_entries_count (whose `work` holds the scanned per-tile head counts): out[nuniq], and --
+// when lo != NULL -- the swapped list of hc_entries_transpose (lo[nuniq], *n_lo) from the same pass.
+extern "C" int hc_entries_emit(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid, const void* work,
+                               int64_t nuniq, int32_t col_bits, int32_t cnt_bits, int32_t unit, unsigned long long* out,
+                               unsigned long long* lo, unsigned long long* n_lo, int32_t* d_overflow, int32_t* h_overflow,
+                               void* stream) {
+    HC_REQUIRE(n >= 0 && nuniq >= 0 && d_overflow != nullptr && h_overflow != nullptr && col_bits > 0 && cnt_bits > 0, "sizes");
+    HC_REQUIRE(lo == nullptr || n_lo != nullptr, "n_lo");
+    cudaStream_t s = (cudaStream_t)stream;
+    *h_overflow = 0;
+    if (lo) HC_CUDA(cudaMemsetAsync(n_lo, 0, sizeof(unsigned long long), s));
+    if (nuniq == 0) return HC_OK;
+    const long long tiles = (n + RLE_TILE - 1) / RLE_TILE;
+    HC_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
+    auto kern = unit ? (lo ? ent_emit_kernel<true, true> : ent_emit_kernel<true, false>)
+                     : (lo ? ent_emit_kernel<false, true> : ent_emit_kernel<false, false>);
+    kern<<<(unsigned)tiles, RLE_THREADS, 0, s>>>(sorted, n_valid, cnt_bits, reinterpret_cast<const int64_t*>(work), out, lo, col_bits,
+                                                 n_lo, d_overflow);
     HC_LAUNCH_CHECK();
     HC_CUDA(cudaMemcpyAsync(h_overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     HC_CUDA(cudaStreamSynchronize(s));

@@ -127,26 +127,22 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
         flag += 1
     else:
         try:
-            up, sent, free = kernels.pairs_to_upper_entries(pairs, res, start, chrom_bins, nbins, cis_only)
-            lists = (up, sent, free)
+            lists = kernels.pairs_to_entry_lists(pairs, res, start, chrom_bins, nbins, cis_only)
         except kernels.CountFieldOverflow:
             flag += 1
     dist.all_reduce(flag)                      # all ranks take the same path
     if int(flag.item()):
         del lists
         return _build_row_block_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only)
-    up, sent, free = lists
+    up, slo, n_lo = lists
     cb, cnt_bits = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
-    nuniq = int(up.numel())
-    tmp = free if (free is not None and free.numel() >= nuniq) else None
-    slo, n_lo = kernels.transpose_entries(up, nbins, lo=sent, tmp=tmp)
     lo = slo[:int(n_lo.item())]
     inbox, cuts = exchange_entry_lists(up, lo, nbins)
-    del up, lo, slo, sent, free, tmp
+    del up, lo, slo, lists
     merged, mfree = kernels.sort_entries(inbox, nbins, cnt_bits, 2)
     nv = torch.tensor([inbox.numel()], dtype=torch.int64, device=dev)
     try:
-        cells = kernels.reduce_entries(merged, nv, nbins, unit=False, scratch=mfree)
+        cells = kernels.reduce_entries(merged, nv, nbins, unit=False)
         ok = 0
     except kernels.CountFieldOverflow:
         ok = 1

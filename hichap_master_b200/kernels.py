@@ -406,43 +406,38 @@ class CountFieldOverflow(OverflowError):
     """A cell count does not fit the count field of the 64-bit entries."""
 
 
-def reduce_entries(sorted_ent, n_valid, nbins: int, unit: bool, scratch=None):
-    """Reduce-by-cell over sorted entries -> reduced entries [nuniq] (a fresh tensor).  ``scratch``: optional int64
-    tensor of >= len(sorted_ent) elements for the head positions (the free half of the sort's ping-pong pair)."""
+def reduce_entries(sorted_ent, n_valid, nbins: int, unit: bool, lower_into=None, want_lower=False):
+    """Reduce-by-cell over sorted entries.  Returns the reduced entries [nuniq] (a fresh tensor) -- and, with
+    ``want_lower``, also (lo [nuniq], n_lo device scalar): the same cells with row and col swapped (padding key for the
+    diagonal ones), written by the same pass into ``lower_into`` when that tensor is large enough."""
     dev, n = sorted_ent.device, int(sorted_ent.numel())
-    cnt_bits = entry_cnt_bits(nbins)
+    cb, cnt_bits = key_col_bits(nbins), entry_cnt_bits(nbins)
+    work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=dev)
+    nuniq = C.c_int64(0)
+    check(lib().hc_entries_count(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), C.byref(nuniq), stream_ptr()),
+          "hc_entries_count")
+    nuniq = int(nuniq.value)
+    out = torch.empty(nuniq, dtype=torch.int64, device=dev)
+    lo = n_lo = None
+    if want_lower:
+        lo = lower_into[:nuniq] if (lower_into is not None and lower_into.numel() >= nuniq) else \
+            torch.empty(nuniq, dtype=torch.int64, device=dev)
+        n_lo = torch.zeros(1, dtype=torch.int64, device=dev)
     d_ovf = torch.zeros(1, dtype=torch.int32, device=dev)
     h_ovf = C.c_int32(0)
-    nuniq = C.c_int64(0)
-    if sorted_ent.data_ptr() % 16 == 0:
-        # one pass: head flags, tile counts and their prefix by decoupled look-back
-        upos = scratch if (scratch is not None and scratch.numel() >= n) else torch.empty(max(n, 1), dtype=torch.int64, device=dev)
-        work = torch.empty(int(lib().hc_entries_heads_work_bytes(n)), dtype=torch.uint8, device=dev)
-        check(lib().hc_entries_heads(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), ptr(upos), C.byref(nuniq),
-                                     stream_ptr()), "hc_entries_heads")
-        nuniq = int(nuniq.value)
-        out = torch.empty(nuniq, dtype=torch.int64, device=dev)
-        check(lib().hc_entries_reduce_at(ptr(sorted_ent), ptr(n_valid), ptr(upos), nuniq, cnt_bits, int(bool(unit)), ptr(out),
-                                         ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce_at")
-    else:
-        # count, scan, emit (three passes; any alignment)
-        work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=dev)
-        check(lib().hc_entries_count(ptr(sorted_ent), n, ptr(n_valid), cnt_bits, ptr(work), C.byref(nuniq), stream_ptr()),
-              "hc_entries_count")
-        nuniq = int(nuniq.value)
-        out = torch.empty(nuniq, dtype=torch.int64, device=dev)
-        upos = torch.empty(max(nuniq, 1), dtype=torch.int64, device=dev)
-        check(lib().hc_entries_reduce(ptr(sorted_ent), n, ptr(n_valid), ptr(work), nuniq, cnt_bits, int(bool(unit)), ptr(upos),
-                                      ptr(out), ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_reduce")
+    check(lib().hc_entries_emit(ptr(sorted_ent), n, ptr(n_valid), ptr(work), nuniq, cb, cnt_bits, int(bool(unit)), ptr(out),
+                                ptr(lo), ptr(n_lo), ptr(d_ovf), C.byref(h_ovf), stream_ptr()), "hc_entries_emit")
     if h_ovf.value:
         raise CountFieldOverflow("a cell holds more than 2^%d - 1 pairs" % cnt_bits)
-    return out
+    return (out, lo, n_lo) if want_lower else out
 
 
-def pairs_to_upper_entries(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
-                           check_bounds=True):
-    """pairs -> one entry per pair (its upper-triangle cell) -> sorted -> reduced.  Returns
-    (up [nuniq] ordered by (row, col), two free int64 scratch tensors of >= pairs.n elements in total)."""
+def pairs_to_entry_lists(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, cis_only: bool,
+                         check_bounds=True):
+    """pairs -> one entry per pair (its upper-triangle cell) -> sorted -> reduced; the lower-triangle list (swapped
+    cells) comes out of the same reduction pass and is re-sorted on its row bits.  Returns (up [nuniq] ordered by
+    (row, col), lo_sorted [nuniq] ordered by (row, col) with the padding keys of the diagonal cells behind the first
+    n_lo entries, n_lo device scalar)."""
     dev = pairs.device
     cb, cnt_bits = key_col_bits(nbins), entry_cnt_bits(nbins)
     ent = torch.empty(max(pairs.n, 1), dtype=torch.int64, device=dev)
@@ -455,9 +450,12 @@ def pairs_to_upper_entries(pairs: PairColumns, res: int, start, chrom_bins, nbin
         _raise_oob(oob, "genome-wide")
     ent = ent[:pairs.n]
     sent, free = sort_entries(ent, nbins, cnt_bits, 2)
-    # the head positions go into the free half of the ping-pong pair
-    up = reduce_entries(sent, n_valid, nbins, unit=True, scratch=free)
-    return up, sent, free
+    # the lower list goes into the free half of the ping-pong pair; the sorted pair entries are dead after the reduction
+    # and serve as the ping-pong partner of the lower list's sort
+    up, lo, n_lo = reduce_entries(sent, n_valid, nbins, unit=True, lower_into=free, want_lower=True)
+    nuniq = int(up.numel())
+    slo, _ = sort_entries(lo, nbins, cnt_bits + cb, 1, tmp=sent[:nuniq] if sent.numel() >= nuniq else None)
+    return up, slo, n_lo
 
 
 def entries_to_csr(up, lo, n_lo, nbins: int, nrows: int, row0: int = 0, total=None):
@@ -524,14 +522,9 @@ def pairs_to_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: int, ci
     if os.environ.get("HC_SORT_KEYS_PER_PAIR", "1") == "2" or pairs.n == 0:
         return _pairs_to_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
     try:
-        up, sent, free = pairs_to_upper_entries(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
+        up, slo, n_lo = pairs_to_entry_lists(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
     except CountFieldOverflow:
         return _pairs_to_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only, check_bounds)
-    nuniq = int(up.numel())
-    # `sent` (the sorted pair entries) and `free` (the head positions) are dead now: they hold the lower list and the
-    # ping-pong partner of its sort
-    tmp = free if (free is not None and free.numel() >= nuniq) else None
-    slo, n_lo = transpose_entries(up, nbins, lo=sent, tmp=tmp)
     row_ptr, col, cnt = entries_to_csr(up, slo, n_lo, nbins, nbins)
     return SymCsr(row_ptr, col, cnt, nbins)
 

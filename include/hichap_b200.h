@@ -281,15 +281,11 @@ int hc_entries_count(const unsigned long long* sorted, int64_t n, const unsigned
 int hc_entries_reduce(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid,
                       const void* work, int64_t nuniq, int32_t cnt_bits, int32_t unit, int64_t* upos /* nuniq */,
                       unsigned long long* out, int32_t* d_overflow, int32_t* h_overflow, void* stream);
-/* The same reduction with the head positions found in ONE pass (flags + tile counts + decoupled look-back): upos (up to n
- * int64) receives the position of the first entry of every distinct cell, *h_nuniq their number (synchronises);
- * hc_entries_reduce_at then writes out[nuniq].  `sorted` must be 16-byte aligned. */
-int64_t hc_entries_heads_work_bytes(int64_t n);
-int hc_entries_heads(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid, int32_t cnt_bits,
-                     void* work, int64_t* upos, int64_t* h_nuniq, void* stream);
-int hc_entries_reduce_at(const unsigned long long* sorted, const unsigned long long* n_valid, const int64_t* upos,
-                         int64_t nuniq, int32_t cnt_bits, int32_t unit, unsigned long long* out, int32_t* d_overflow,
-                         int32_t* h_overflow, void* stream);
+/* The default reduction: after hc_entries_count (whose `work` keeps the scanned per-tile head counts), ONE pass writes
+ * out[nuniq] and, when lo != NULL, the swapped list of hc_entries_transpose (lo[nuniq], *n_lo) as well. */
+int hc_entries_emit(const unsigned long long* sorted, int64_t n, const unsigned long long* n_valid, const void* work,
+                    int64_t nuniq, int32_t col_bits, int32_t cnt_bits, int32_t unit, unsigned long long* out,
+                    unsigned long long* lo, unsigned long long* n_lo, int32_t* d_overflow, int32_t* h_overflow, void* stream);
 int hc_entries_transpose(const unsigned long long* up, int64_t n, int32_t col_bits, int32_t cnt_bits,
                          unsigned long long* lo, unsigned long long* n_lo, void* stream);
 int64_t hc_entries_csr_work_bytes(int64_t nrows);

@@ -276,7 +276,7 @@ def test_entry_count_field_overflow_falls_back(K, cuda_device, monkeypatch):
     chrom_bins = torch.tensor([nb], dtype=torch.int32, device=cuda_device)
     pairs = PairColumns(c1, p1, c1, p2, device=cuda_device)
     with pytest.raises(K.CountFieldOverflow):
-        K.pairs_to_upper_entries(pairs, res, start, chrom_bins, nb, False)
+        K.pairs_to_entry_lists(pairs, res, start, chrom_bins, nb, False)
     csr = K.pairs_to_csr(pairs, res, start, chrom_bins, nb, False)
     M = np.zeros((nb, nb), np.int64)
     np.add.at(M, (p1 // res, p2 // res), 1)
@@ -299,8 +299,50 @@ def test_reduce_entries_adds_counts(K, cuda_device):
     t = torch.from_numpy(ent.astype(np.int64)).to(cuda_device)
     sent, free = K.sort_entries(t, nb, vb, 2)
     nv = torch.tensor([ent.size], dtype=torch.int64, device=cuda_device)
-    got = K.reduce_entries(sent, nv, nb, unit=False, scratch=free).cpu().numpy()
+    got = K.reduce_entries(sent, nv, nb, unit=False).cpu().numpy()
     key = (r << cb) | c
     uk, inv = np.unique(key, return_inverse=True)
     tot = np.bincount(inv, weights=v).astype(np.int64)
     assert np.array_equal(got >> vb, uk) and np.array_equal(got & ((1 << vb) - 1), tot)
+
+
+def test_fused_emit_equals_unfused_building_blocks(K, cuda_device):
+    """hc_entries_emit (reduce + transpose in one pass) against hc_entries_reduce followed by hc_entries_transpose, on a list
+    with runs that cross warp chunks and tiles (one cell holds 20 000 pairs) and padding entries."""
+    import ctypes as C
+    import torch
+    from hichap_master_b200._abi import check, lib
+    from hichap_master_b200.device import ptr, stream_ptr
+    nb = 3000
+    cb, vb = K.key_col_bits(nb), K.entry_cnt_bits(nb)
+    rng = np.random.default_rng(11)
+    r = rng.integers(0, nb, 150_000); c = np.minimum(r + rng.integers(0, 50, r.size), nb - 1)
+    r[:20_000] = 7; c[:20_000] = 9                      # a long run
+    r[20_000:21_000] = 100; c[20_000:21_000] = 100      # a diagonal cell
+    ent = (((r << cb) | c) << vb) | 1
+    ent = np.concatenate([ent, np.full(5_000, -1, np.int64)])       # padding keys (dropped pairs)
+    rng.shuffle(ent)
+    t = torch.from_numpy(ent.astype(np.int64)).to(cuda_device)
+    sent, free = K.sort_entries(t, nb, vb, 2)
+    nv = torch.tensor([r.size], dtype=torch.int64, device=cuda_device)
+    up, lo, n_lo = K.reduce_entries(sent, nv, nb, unit=True, want_lower=True)
+    # unfused
+    n = int(sent.numel())
+    work = torch.empty(int(lib().hc_csr_work_bytes(n)), dtype=torch.uint8, device=cuda_device)
+    nu = C.c_int64(0)
+    check(lib().hc_entries_count(ptr(sent), n, ptr(nv), vb, ptr(work), C.byref(nu), stream_ptr()), "count")
+    nu = int(nu.value)
+    assert nu == up.numel()
+    out2 = torch.empty(nu, dtype=torch.int64, device=cuda_device)
+    upos = torch.empty(nu, dtype=torch.int64, device=cuda_device)
+    d_ovf = torch.zeros(1, dtype=torch.int32, device=cuda_device); h_ovf = C.c_int32(0)
+    check(lib().hc_entries_reduce(ptr(sent), n, ptr(nv), ptr(work), nu, vb, 1, ptr(upos), ptr(out2), ptr(d_ovf), C.byref(h_ovf),
+                                  stream_ptr()), "reduce")
+    lo2 = torch.empty(nu, dtype=torch.int64, device=cuda_device)
+    n_lo2 = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    check(lib().hc_entries_transpose(ptr(out2), nu, cb, vb, ptr(lo2), ptr(n_lo2), stream_ptr()), "transpose")
+    assert torch.equal(up, out2) and torch.equal(lo, lo2) and int(n_lo.item()) == int(n_lo2.item())
+    key = (r << cb) | c
+    uk, cnts = np.unique(key, return_counts=True)
+    got = up.cpu().numpy()
+    assert np.array_equal(got >> vb, uk) and np.array_equal(got & ((1 << vb) - 1), cnts)
