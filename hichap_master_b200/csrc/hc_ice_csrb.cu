@@ -682,6 +682,13 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
     std::vector<int64_t> h_tot(nb + 1, 0);
     if (nloc > 0) {
         const int nsb = (int)((nseg + SCAN_BLOCK - 1) / SCAN_BLOCK);
+        // The entry buffer is by far the largest scratch block (3.9 GB on C4) and is requested FIRST, with an upper bound on
+        // its size (every non-empty segment pads at most 3 entries): requested after the smaller blocks, it found the pool's
+        // big free block nibbled by them every other call and paid ~30 ms for fresh mappings (profiles/r3d_c4ice.json).
+        int64_t h_nnz = 0;
+        HC_CUDA(hc_read_small(&h_nnz, row_ptr + nloc, sizeof(int64_t), s));
+        const long long ent_cap = std::max(4ll, (long long)h_nnz + 3 * std::min<long long>(nseg, (long long)h_nnz));
+        HC_CUDA(scratch.alloc((void**)&d_ent, sizeof(uint32_t) * (size_t)ent_cap));
         HC_CUDA(scratch.alloc((void**)&d_start, sizeof(int64_t) * nseg));
         HC_CUDA(scratch.alloc((void**)&d_seg, sizeof(int64_t) * (nseg + 4)));      // + slack: the bulk copies of the bounds are 16-byte granular
         HC_CUDA(scratch.alloc((void**)&d_bsum, sizeof(int64_t) * (nsb + 1 + nb + 1) + 16));
@@ -702,7 +709,7 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         HC_LAUNCH_CHECK();
         HC_CUDA(hc_read_small(h_tot.data(), d_tot, sizeof(int64_t) * (nb + 1), s));
         total_ent = h_tot[nb];
-        HC_CUDA(scratch.alloc((void**)&d_ent, sizeof(uint32_t) * (size_t)std::max(total_ent, 4ll)));
+        HC_REQUIRE(total_ent <= ent_cap, "internal: entry bound");
         HC_CUDA(cudaMemsetAsync(d_ent, 0, sizeof(uint32_t) * (size_t)std::max(total_ent, 4ll), s));
         csrb_fill_kernel<<<(unsigned)((nloc * 32 + 255) / 256), 256, 0, s>>>(row_ptr, col, cnt, row0, nloc, P->ignore_diags, d_start,
                                                                              d_seg, d_ent, d_flag);

@@ -16,8 +16,7 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #define HC_SORT_DEFAULT_THREADS 512
 #endif
 constexpr int SORT_DEFAULT_THREADS = HC_SORT_DEFAULT_THREADS;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_MIN_TILE = 256 * SORT_ITEMS;       // 4096 keys = 32 KB
+constexpr int SORT_MIN_TILE = 256 * 16;               // smallest tile of any variant (sizes the status array)
 constexpr int MAX_PASSES = 8;
 #ifndef HC_SORT_MIN_BLOCKS
 #define HC_SORT_MIN_BLOCKS 4
@@ -78,7 +77,7 @@ __global__ void __launch_bounds__(RADIX) radix_scan_kernel(unsigned long long* _
 // THREADS x 16 keys per tile.  The tile size sets the length of the digit runs a tile writes (tile / 256 keys on a
 // uniform digit): 128 B runs at 4096 keys, 256 B at 8192 -- the low-digit passes are bound by those scattered writes
 // (measured 2.1 TB/s at 4096 against 3.3 TB/s for the top digit, whose 64 occupied bins give 512 B runs).
-template <int THREADS>
+template <int THREADS, int SORT_ITEMS>
 struct SortSmemT {
     unsigned long long keys[THREADS * SORT_ITEMS];
     unsigned int warp_hist[THREADS / 32][RADIX];
@@ -104,14 +103,14 @@ __device__ __forceinline__ unsigned match_digit(unsigned d, bool ok) {
     return m;
 }
 
-template <int SORT_LOOKBACK, int THREADS, int MINB, bool BALLOT>
+template <int SORT_LOOKBACK, int THREADS, int MINB, bool BALLOT, int SORT_ITEMS>
 __global__ void __launch_bounds__(THREADS, MINB)
 radix_onesweep_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
                       int shift, const unsigned long long* __restrict__ digit_base /*[256]*/,
                       unsigned long long* status /*[num_tiles][256]*/, unsigned int* tile_counter) {
     constexpr int WARPS = THREADS / 32, TILE = THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmemT<THREADS>& sm = *reinterpret_cast<SortSmemT<THREADS>*>(smem_raw);
+    SortSmemT<THREADS, SORT_ITEMS>& sm = *reinterpret_cast<SortSmemT<THREADS, SORT_ITEMS>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) sm.tile_id = atomicAdd(tile_counter, 1u);   // tiles are claimed in launch order
     for (int i = tid; i < WARPS * RADIX; i += THREADS) (&sm.warp_hist[0][0])[i] = 0;
@@ -267,7 +266,8 @@ extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tm
     HC_LAUNCH_CHECK();
 
     // variants: HC_SORT_LOOKBACK = 1 | 8 status words fetched per look-back step; HC_SORT_THREADS = 256 | 512 threads per tile
-    // (4096 / 8192 keys); HC_SORT_MATCH = any | ballot
+    // (4096 / 8192 keys); HC_SORT_MATCH = any | ballot.  (12 keys per thread at five CTAs of 256 threads per SM was measured
+    // too: 19.9 against 17.3 ms per 500 M keys.)
     static const int lookback = [] { const char* e = getenv("HC_SORT_LOOKBACK"); return (e && atoi(e) == 1) ? 1 : 8; }();
     static const int threads = [] { const char* e = getenv("HC_SORT_THREADS"); const int v = e ? atoi(e) : SORT_DEFAULT_THREADS;
                                     return (v == 256 || v == 512) ? v : SORT_DEFAULT_THREADS; }();
@@ -275,13 +275,13 @@ extern "C" int hc_sort_keys_u64(unsigned long long* keys, unsigned long long* tm
     using Kern = void (*)(const unsigned long long*, unsigned long long*, long long, int, const unsigned long long*,
                           unsigned long long*, unsigned int*);
     static const Kern table[2][2][2] = {
-        {{radix_onesweep_kernel<1, 256, 4, false>, radix_onesweep_kernel<1, 256, 4, true>},
-         {radix_onesweep_kernel<8, 256, 4, false>, radix_onesweep_kernel<8, 256, 4, true>}},
-        {{radix_onesweep_kernel<1, 512, 2, false>, radix_onesweep_kernel<1, 512, 2, true>},
-         {radix_onesweep_kernel<8, 512, 2, false>, radix_onesweep_kernel<8, 512, 2, true>}}};
+        {{radix_onesweep_kernel<1, 256, 4, false, 16>, radix_onesweep_kernel<1, 256, 4, true, 16>},
+         {radix_onesweep_kernel<8, 256, 4, false, 16>, radix_onesweep_kernel<8, 256, 4, true, 16>}},
+        {{radix_onesweep_kernel<1, 512, 2, false, 16>, radix_onesweep_kernel<1, 512, 2, true, 16>},
+         {radix_onesweep_kernel<8, 512, 2, false, 16>, radix_onesweep_kernel<8, 512, 2, true, 16>}}};
     const Kern kern = table[threads == 256 ? 0 : 1][lookback == 1 ? 0 : 1][ballot ? 1 : 0];
-    const size_t smem = threads == 256 ? sizeof(SortSmemT<256>) : sizeof(SortSmemT<512>);
-    const long long tile_keys = (long long)threads * SORT_ITEMS;
+    const size_t smem = threads == 256 ? sizeof(SortSmemT<256, 16>) : sizeof(SortSmemT<512, 16>);
+    const long long tile_keys = (long long)threads * 16;
     const long long tiles = (n + tile_keys - 1) / tile_keys;
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long* src = keys;
