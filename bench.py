@@ -560,6 +560,7 @@ def run_c4_section(args, world, rank, dev, peak, config="C4", standalone=False):
     pairs = PairColumns(c1, p1, c2, p2, device=dev)
     del c1, p1, c2, p2
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()                   # the generator's temporaries (several times the pair columns)
 
     def sync_all():
         if world > 1:

@@ -575,6 +575,11 @@ def ice_balance_csr(csr: SymCsr, prob_off, chrom_off=None, comm=None, allreduce=
     res = torch.zeros(nprob * C.sizeof(IceResult), dtype=torch.uint8, device=dev)
     info = IceRunInfo(0, 0.0)
     h_off = (C.c_int64 * len(prob_off))(*[int(x) for x in prob_off])
+    # the library re-encodes the CSR into stream-ordered scratch of its own (~4.3 B per stored entry + ~100 B per row and
+    # column block): hand torch's cached-but-unused blocks back to the driver first when the device could not serve that
+    need = int(4.3 * csr.nnz) + 16 * csr.nloc * ((n + 8191) // 8192) + (64 << 20)
+    if torch.cuda.mem_get_info(dev)[0] < need:
+        torch.cuda.empty_cache()
     check(lib().hc_ice_csr_balance(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.row0, csr.nloc, ptr(d_prob),
                                    nprob, h_off, C.byref(params), ptr(bias), ptr(work), ptr(res), C.byref(info),
                                    C.c_void_p(comm or 0), stream_ptr()), "hc_ice_csr_balance")
