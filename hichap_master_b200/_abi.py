@@ -43,6 +43,7 @@ _P, _I32, _I64 = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
     "hc_version": (C.c_int, []),
     "hc_init": (C.c_int, []),
+    "hc_mempool_free_bytes": (C.c_int64, []),
     "hc_last_error": (C.c_char_p, []),
     "hc_launch_count": (C.c_int64, []),
     "hc_bin_pairs_local": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P]),

@@ -33,6 +33,19 @@ extern "C" int hc_init(void) {
     return HC_OK;
 }
 
+// Bytes the default stream-ordered pool holds but does not use right now (what a cudaMallocAsync can get without asking the
+// driver): lets a caller that shares the device with another allocator decide whether that one has to give memory back.
+extern "C" int64_t hc_mempool_free_bytes(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return 0;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) return 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) return 0;
+    return reserved > used ? (int64_t)(reserved - used) : 0;
+}
+
 // Small device -> host reads (a convergence counter, a few offsets) that must not queue behind a
 // large cudaMemcpy on the device-to-host copy engine -- the upper-triangular records (1.4 GB for
 // C2) are copied out while the ICE loop runs, and a 4-byte cudaMemcpyAsync poll issued meanwhile

@@ -222,10 +222,14 @@ __device__ __forceinline__ void load_tile_fast(const int32_t* __restrict__ X, in
 // flag, 1 / s) is staged once per tile in shared memory / registers; cells outside the matrix are zero in the staged
 // tiles and have 1 / alpha = 0, so they need no test.  (The first version evaluated bounds, flags and the 1 / alpha
 // loads per cell: 31 thread instructions per cell, issue-bound at 2.6 TB/s -- profiles/r1d_ncu_secondary_raw.csv.)
-template <int PASS, bool GAP>
+// DIAG: the tile pair is a diagonal tile (I == J: one tile, read at both orientations, leading dimension T); otherwise the
+// transposed operand is the padded copy of tile (J, I) -- compile-time so that the inner loop carries neither the diagonal
+// test nor a run-time leading dimension (the ROWSUM / TOTAL passes are issue-bound)
+template <int PASS, bool GAP, bool DIAG>
 __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, int r0, int c0, const int32_t* sA, const int32_t* tB,
-                                              int ldb, const double* vr, const double* vc, double* sV, double (*colred)[T], double* red,
+                                              const double* vr, const double* vc, double* sV, double (*colred)[T], double* red,
                                               int cta) {
+    constexpr int ldb = DIAG ? T : LDB;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps; a warp covers one tile row at a time
     // per-column values of this thread's two columns
     double raj[2], rsj[2];
@@ -257,7 +261,7 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
             double sym;
             if (GAP) sym = (gi && gj[b]) ? fmax(sij, sji) : (sij + sji) * 0.5;
             else sym = sij + sji;
-            if (I == J && r == c) sym = sij;
+            if (DIAG && r == c) sym = sij;
             if (PASS == PASS_ROWSUM) { rsum += sym; colp[b] += sym; }
             else {
                 const double cor = sym * (rsi * rsj[b]);
@@ -293,7 +297,7 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
                 a.partial[(int64_t)J * np + r0 + ty + 8 * ai] = w1;            // rows of block I, other block J
             }
         }
-        if (I != J) {
+        if (!DIAG) {
             colred[ty][tx] = colp[0]; colred[ty][tx + 32] = colp[1];
             __syncthreads();
             if (threadIdx.x < T) {
@@ -305,10 +309,10 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
         }
     } else if (PASS == PASS_TOTAL) {
         const double s = block_sum(tot, red);
-        if (threadIdx.x == 0) a.cta_partial[cta] = (I != J) ? 2.0 * s : s;
+        if (threadIdx.x == 0) a.cta_partial[cta] = DIAG ? s : 2.0 * s;
     } else {
         const double rf = a.scalars[0];
-        if (I != J) __syncthreads();          // sV aliases sA / sB: every thread is done reading them
+        if (!DIAG) __syncthreads();          // sV aliases sA / sB: every thread is done reading them
 #pragma unroll
         for (int ai = 0; ai < 8; ++ai) {
             const int r = ty + 8 * ai, gi = r0 + r;
@@ -317,10 +321,10 @@ __device__ __forceinline__ void sym_pass_body(const SymArgs& a, int I, int J, in
                 const int c = tx + 32 * b, gjj = c0 + c;
                 const double v = rf * val[ai][b];
                 if (gi < a.n && gjj < a.n) a.out[(int64_t)gi * a.ld_out + gjj] = v;
-                if (I != J) sV[c * LDB + r] = v;
+                if (!DIAG) sV[c * LDB + r] = v;
             }
         }
-        if (I != J) {
+        if (!DIAG) {
             __syncthreads();
 #pragma unroll
             for (int ai = 0; ai < 8; ++ai) {
@@ -369,14 +373,17 @@ __device__ __forceinline__ void sym_pass_run(SymArgs a, int cta) {
         v[2 * T + t] = (a.has_gap && gidx < a.n && a.gapflag[gidx]) ? 1.0 : 0.0;
     }
     __syncthreads();
-    const int32_t* tB = (I != J) ? sB : sA;
-    const int ldb = (I != J) ? LDB : T;
-    if (a.has_gap) sym_pass_body<PASS, true>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red, cta);
-    else sym_pass_body<PASS, false>(a, I, J, r0, c0, sA, tB, ldb, vr, vc, sV, colred, red, cta);
+    if (I != J) {
+        if (a.has_gap) sym_pass_body<PASS, true, false>(a, I, J, r0, c0, sA, sB, vr, vc, sV, colred, red, cta);
+        else sym_pass_body<PASS, false, false>(a, I, J, r0, c0, sA, sB, vr, vc, sV, colred, red, cta);
+    } else {
+        if (a.has_gap) sym_pass_body<PASS, true, true>(a, I, J, r0, c0, sA, sA, vr, vc, sV, colred, red, cta);
+        else sym_pass_body<PASS, false, true>(a, I, J, r0, c0, sA, sA, vr, vc, sV, colred, red, cta);
+    }
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(TS_THREADS) sym_pass_kernel(SymArgs a) { sym_pass_run<PASS>(a, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TS_THREADS, PASS == PASS_WRITE ? 4 : 5) sym_pass_kernel(SymArgs a) { sym_pass_run<PASS>(a, (int)blockIdx.x); }
 
 // ---- all matrices of a batch in one launch per pass -------------------------------------------
 // (46 matrices x 6 dependent launches, most of them small, cost 1.1 ms of launch-latency chains out of 5.8 ms --
@@ -395,7 +402,7 @@ __device__ __forceinline__ int batch_find(const int* __restrict__ off, int nmat,
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(TS_THREADS) sym_pass_batch_kernel(SymBatch b) {
+__global__ void __launch_bounds__(TS_THREADS, PASS == PASS_WRITE ? 4 : 5) sym_pass_batch_kernel(SymBatch b) {
     const int k = batch_find(b.pair_off, b.nmat, (int)blockIdx.x);
     sym_pass_run<PASS>(b.mats[k], (int)blockIdx.x - b.pair_off[k]);
 }

@@ -119,8 +119,17 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     their owner; the owner sorts what it received once more and adds the counts of equal cells -- the cells travel
     reduced, and a row's lower and upper parts interleave into CSR order by that one sort."""
     import os
+    import time
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = pairs.device
+    timing = os.environ.get("HC_DIST_TIMING") == "1"      # per-phase wall times of this rank on stderr (synchronises)
+    marks = []
+
+    def mark(what):
+        if timing:
+            torch.cuda.synchronize(dev)
+            marks.append((what, time.perf_counter()))
+    mark("start")
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     lists = None
     if os.environ.get("HC_SORT_KEYS_PER_PAIR", "1") == "2":
@@ -135,11 +144,14 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
         del lists
         return _build_row_block_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only)
     up, slo, n_lo = lists
+    mark("local lists (entries, sort, reduce, lower sort)")
     cb, cnt_bits = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
     lo = slo[:int(n_lo.item())]
     inbox, cuts = exchange_entry_lists(up, lo, nbins)
+    mark("cuts + exchange")
     del up, lo, slo, lists
     merged, mfree = kernels.sort_entries(inbox, nbins, cnt_bits, 2)
+    mark("merge sort of the inbox (%d entries)" % int(inbox.numel()))
     nv = torch.tensor([inbox.numel()], dtype=torch.int64, device=dev)
     try:
         cells = kernels.reduce_entries(merged, nv, nbins, unit=False)
@@ -150,6 +162,12 @@ def build_row_block_csr(pairs: PairColumns, res: int, start, chrom_bins, nbins: 
     dist.all_reduce(flag)
     if int(flag.item()):
         return _build_row_block_csr_two_keys(pairs, res, start, chrom_bins, nbins, cis_only)
+    mark("add-counts reduce")
     row0, row1 = cuts[rank], cuts[rank + 1]
     row_ptr, col, cnt = kernels.entries_to_csr(cells, None, None, nbins, row1 - row0, row0=row0, total=int(cells.numel()))
+    mark("CSR")
+    if timing:
+        import sys
+        sys.stderr.write("[build_row_block_csr rank %d] " % rank + "; ".join(
+            "%s %.2f ms" % (marks[i][0], 1e3 * (marks[i][1] - marks[i - 1][1])) for i in range(1, len(marks))) + "\n")
     return kernels.SymCsr(row_ptr, col, cnt, nbins, row0=row0), cuts

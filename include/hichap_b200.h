@@ -39,6 +39,8 @@ extern "C" {
 int hc_version(void);
 /* Optional, once per device: keep the library's stream-ordered scratch cached between calls. */
 int hc_init(void);
+/* Bytes the library's stream-ordered pool (the default cudaMallocAsync pool, kept by hc_init) holds without using them. */
+int64_t hc_mempool_free_bytes(void);
 const char* hc_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 int64_t hc_launch_count(void);
