@@ -1114,7 +1114,8 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
                                                                       P->min_count, do_mad, bias);
     HC_LAUNCH_CHECK();
     if (do_mad) {
-        static const bool single = [] { const char* e = getenv("HC_ICE_MAD_SINGLE"); return e && atoi(e) != 0; }();
+        const char* e_single = getenv("HC_ICE_MAD_SINGLE");
+        const bool single = e_single && atoi(e_single) != 0;
         if (single) {
             ice_filter_mad_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(marg, nbins, P->mad_max, bias, work);
             HC_LAUNCH_CHECK();

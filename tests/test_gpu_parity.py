@@ -548,3 +548,45 @@ def test_stage_from_host_chunks_equals_whole_upload(mb, cuda_device, n, chunk):
         assert np.array_equal(st.batch.to_numpy(i), tiles1[i]) and np.array_equal(tiles1[i], exp[i])
         assert np.array_equal(o2["records"][i], rec1[i])
     assert np.array_equal(o2["bias"].cpu().numpy(), w1, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,seed", [(5, 0), (1000, 1), (70_001, 2), (300_000, 3)])
+def test_mad_filter_grid_wide_equals_single_cta_and_numpy(mb, cuda_device, monkeypatch, n, seed):
+    """hc_ice_filter_bins: the grid-wide radix select (default) against the single-CTA kernel (HC_ICE_MAD_SINGLE=1) and
+    against NumPy's medians -- marginals with ties, zeros (excluded bins) and a heavy tail; the bias masks must be equal."""
+    import ctypes as C
+    import torch
+    from hichap_master_b200 import kernels
+    from hichap_master_b200._abi import check, lib
+    from hichap_master_b200.device import ptr, stream_ptr
+    rng = np.random.default_rng(seed)
+    marg = np.exp(rng.normal(0, 0.4, n)) * 1000
+    marg[rng.random(n) < 0.1] = 0.0                         # uncovered bins
+    marg[rng.random(n) < 0.05] *= 1e-3                      # low outliers (what MAD-max removes)
+    marg[::7] = np.round(marg[::7])                         # ties
+    nnz = np.full(n, 100.0)
+    chrom_off = np.array([0, n // 3, n], np.int64)
+    params = kernels.ice_params(mad_max=5, min_nnz=10)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("HC_ICE_MAD_SINGLE", mode)
+        t = lambda a: torch.from_numpy(a.copy()).to(cuda_device)
+        d_nnz, d_marg, d_off = t(nnz), t(marg), t(chrom_off)
+        bias = torch.empty(n, dtype=torch.float64, device=cuda_device)
+        work = torch.empty(2 * n, dtype=torch.float64, device=cuda_device)
+        check(lib().hc_ice_filter_bins(ptr(d_nnz), ptr(d_marg), n, ptr(d_off), 2, C.byref(params), ptr(bias), ptr(work),
+                                       stream_ptr()), "hc_ice_filter_bins")
+        out[mode] = bias.cpu().numpy()
+    assert np.array_equal(out["0"], out["1"])
+    # cooler's rule in NumPy
+    m = marg.copy()
+    for lo, hi in zip(chrom_off[:-1], chrom_off[1:]):
+        c = m[lo:hi]
+        m[lo:hi] = c / np.median(c[c > 0])
+    lg = np.log(m[m > 0])
+    med = np.median(lg)
+    mad = np.median(np.abs(lg - med))
+    cutoff = np.exp(med - 5 * mad)
+    exp = np.ones(n)
+    exp[m < cutoff] = 0.0
+    assert np.array_equal(out["0"], exp)
