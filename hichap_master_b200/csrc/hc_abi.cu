@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include "hc_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -33,6 +34,29 @@ extern "C" int hc_init(void) {
     return HC_OK;
 }
 
+// A second stream-ordered pool for the few multi-GB scratch blocks (the column-blocked CSR entries): in the default pool a
+// 1 KB allocation of another call can be carved out of the big free block, and the next big request then pays ~200 ms for
+// fresh mappings although "enough" memory is free (measured in bench.py: C4 ICE 238 instead of 59 ms).  Nothing small is
+// ever allocated here, so a block of the previous size is found whole.
+cudaMemPool_t hc_big_pool(void) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { (void)cudaGetLastError(); pools[dev] = nullptr; return nullptr; }
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return pools[dev];
+}
+
 // Bytes the default stream-ordered pool holds but does not use right now (what a cudaMallocAsync can get without asking the
 // driver): lets a caller that shares the device with another allocator decide whether that one has to give memory back.
 extern "C" int64_t hc_mempool_free_bytes(void) {
@@ -43,7 +67,13 @@ extern "C" int64_t hc_mempool_free_bytes(void) {
     unsigned long long reserved = 0, used = 0;
     if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) return 0;
     if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) return 0;
-    return reserved > used ? (int64_t)(reserved - used) : 0;
+    int64_t freeb = reserved > used ? (int64_t)(reserved - used) : 0;
+    if (cudaMemPool_t big = hc_big_pool()) {
+        unsigned long long r2 = 0, u2 = 0;
+        if (cudaMemPoolGetAttribute(big, cudaMemPoolAttrReservedMemCurrent, &r2) == cudaSuccess &&
+            cudaMemPoolGetAttribute(big, cudaMemPoolAttrUsedMemCurrent, &u2) == cudaSuccess && r2 > u2) freeb += (int64_t)(r2 - u2);
+    }
+    return freeb;
 }
 
 // Small device -> host reads (a convergence counter, a few offsets) that must not queue behind a

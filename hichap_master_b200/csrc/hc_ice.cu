@@ -1122,8 +1122,20 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
             return HC_OK;
         }
         cudaStream_t s = (cudaStream_t)stream;
-        MadState* st = nullptr;
-        HC_CUDA(cudaMallocAsync(&st, sizeof(MadState), s));
+        // the 1 KB select state lives in a per-thread buffer that is kept between calls: a stream-ordered allocation here was
+        // carved out of the default pool's largest free block and cost the next multi-MB request of another call fresh mappings
+        struct MadCache { MadState* p = nullptr; int dev = -1; cudaStream_t last = nullptr; bool used = false; };
+        static thread_local MadCache mc;
+        int dev = 0;
+        HC_CUDA(cudaGetDevice(&dev));
+        if (mc.p == nullptr || mc.dev != dev) {
+            if (mc.p) { cudaFree(mc.p); mc.p = nullptr; }
+            HC_CUDA(cudaMalloc(reinterpret_cast<void**>(&mc.p), sizeof(MadState)));
+            mc.dev = dev; mc.used = false;
+        }
+        if (mc.used && mc.last != s) HC_CUDA(cudaStreamSynchronize(mc.last));     // the previous call ran on another stream
+        mc.last = s; mc.used = true;
+        MadState* st = mc.p;
         HC_CUDA(cudaMemsetAsync(st, 0, sizeof(MadState), s));
         double* lg = work;
         unsigned long long* keys = reinterpret_cast<unsigned long long*>(work + nbins);
@@ -1139,7 +1151,6 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
         mad_median_kernel<1><<<g, MAD_THREADS, 0, s>>>(keys, nbins, st);
         mad_apply_kernel<<<g, MAD_THREADS, 0, s>>>(marg, nbins, P->mad_max, st, bias);
         HC_LAUNCH_CHECK();
-        HC_CUDA(cudaFreeAsync(st, s));
     }
     return HC_OK;
 }

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <vector>
 #include "hc_common.cuh"
+#include <chrono>
 
 int hc_nccl_allreduce_f64(void* comm, const double* send, double* recv, size_t count, cudaStream_t s);  // hc_nccl.cu
 
@@ -638,6 +639,13 @@ struct Scratch {
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
+    cudaError_t alloc_big(void** p, size_t bytes) {      // from the pool that only holds multi-GB blocks (hc_big_pool)
+        cudaMemPool_t pool = hc_big_pool();
+        if (!pool) return alloc(p, bytes);
+        const cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, s);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
     void release(void* p) {
         for (auto& q : ptrs) if (q == p) { cudaFreeAsync(p, s); q = nullptr; }
     }
@@ -669,6 +677,16 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         cudaEventDestroy(e_in);
     }
     Scratch scratch(s);
+    const bool trace = getenv("HC_DEBUG_MEM") != nullptr && atoi(getenv("HC_DEBUG_MEM")) != 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[csrb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    tick("enter");
     cudaEvent_t evb0 = nullptr, evb1 = nullptr, ev0 = nullptr, ev1 = nullptr;
     struct EvGuard { cudaEvent_t* e[4]; ~EvGuard() { for (auto p : e) if (*p) cudaEventDestroy(*p); } } evg{{&evb0, &evb1, &ev0, &ev1}};
     if (h_info) { cudaEventCreate(&evb0); cudaEventCreate(&evb1); cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(evb0, s); }
@@ -682,13 +700,16 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
     std::vector<int64_t> h_tot(nb + 1, 0);
     if (nloc > 0) {
         const int nsb = (int)((nseg + SCAN_BLOCK - 1) / SCAN_BLOCK);
-        // The entry buffer is by far the largest scratch block (3.9 GB on C4) and is requested FIRST, with an upper bound on
-        // its size (every non-empty segment pads at most 3 entries): requested after the smaller blocks, it found the pool's
-        // big free block nibbled by them every other call and paid ~30 ms for fresh mappings (profiles/r3d_c4ice.json).
+        // The entry buffer is by far the largest scratch block (3.9 GB on C4).  It is requested FIRST, with an upper bound on
+        // its size (every non-empty segment pads at most 3 entries), and from a pool of its own (hc_big_pool): in the default
+        // pool smaller requests -- of this call or of another one -- were carved out of the big free block, and the next big
+        // request paid 30-200 ms for fresh mappings (profiles/r3d_c4ice.json; 238 instead of 59 ms inside bench.py).
         int64_t h_nnz = 0;
         HC_CUDA(hc_read_small(&h_nnz, row_ptr + nloc, sizeof(int64_t), s));
         const long long ent_cap = std::max(4ll, (long long)h_nnz + 3 * std::min<long long>(nseg, (long long)h_nnz));
-        HC_CUDA(scratch.alloc((void**)&d_ent, sizeof(uint32_t) * (size_t)ent_cap));
+        tick("read nnz");
+        HC_CUDA(scratch.alloc_big((void**)&d_ent, sizeof(uint32_t) * (size_t)ent_cap));
+        tick("alloc entries");
         HC_CUDA(scratch.alloc((void**)&d_start, sizeof(int64_t) * nseg));
         HC_CUDA(scratch.alloc((void**)&d_seg, sizeof(int64_t) * (nseg + 4)));      // + slack: the bulk copies of the bounds are 16-byte granular
         HC_CUDA(scratch.alloc((void**)&d_bsum, sizeof(int64_t) * (nsb + 1 + nb + 1) + 16));
@@ -708,12 +729,14 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         csrb_block_totals_kernel<<<(nb + 1 + 255) / 256, 256, 0, s>>>(d_seg, nloc, nb, d_tot);
         HC_LAUNCH_CHECK();
         HC_CUDA(hc_read_small(h_tot.data(), d_tot, sizeof(int64_t) * (nb + 1), s));
+        tick("start/len/scan");
         total_ent = h_tot[nb];
         HC_REQUIRE(total_ent <= ent_cap, "internal: entry bound");
         HC_CUDA(cudaMemsetAsync(d_ent, 0, sizeof(uint32_t) * (size_t)std::max(total_ent, 4ll), s));
         csrb_fill_kernel<<<(unsigned)((nloc * 32 + 255) / 256), 256, 0, s>>>(row_ptr, col, cnt, row0, nloc, P->ignore_diags, d_start,
                                                                              d_seg, d_ent, d_flag);
         HC_LAUNCH_CHECK();
+        tick("memset + fill");
         scratch.release(d_start);
         d_start = nullptr;
     }
@@ -778,6 +801,7 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         HC_LAUNCH_CHECK();
     }
     HC_CUDA(cudaStreamSynchronize(s));             // h_first goes out of use
+    tick("flag + items");
 
     // ---- vectors and bookkeeping ---------------------------------------------------------------------------
     double* d_vec = nullptr;        // bias_pad[nb*CB] | marg[nbins] | marg_local[nbins] (sharded only)
@@ -803,6 +827,7 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
     HC_CUDA(cudaMemcpyAsync(d_book, h_book.data(), sizeof(int32_t) * (nprob + 4), cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaMemcpyAsync(results, h_res.data(), sizeof(hc_ice_result) * nprob, cudaMemcpyHostToDevice, s));
     HC_CUDA(cudaStreamSynchronize(s));
+    tick("vectors + book");
     if (h_info && evb1) cudaEventRecord(evb1, s);
 
     CsrbArgs A;
@@ -862,6 +887,7 @@ int hc_ice_csr_balance_blocked(const int64_t* row_ptr, const int32_t* col, const
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess) { gexec = nullptr; (void)cudaGetLastError(); }
     }
+    tick("graph capture");
     if (h_info && ev0) cudaEventRecord(ev0, s);
     int launches = 0, h_done = 0;
     double stream_ms_sum = 0.0;

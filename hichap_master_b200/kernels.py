@@ -578,7 +578,12 @@ def ice_balance_csr(csr: SymCsr, prob_off, chrom_off=None, comm=None, allreduce=
     # the library re-encodes the CSR into stream-ordered scratch of its own (~4.3 B per stored entry + ~100 B per row and
     # column block): hand torch's cached-but-unused blocks back to the driver first when the device could not serve that
     need = int(4.3 * csr.nnz) + 16 * csr.nloc * ((n + 8191) // 8192) + (64 << 20)
-    if torch.cuda.mem_get_info(dev)[0] + int(lib().hc_mempool_free_bytes()) < need:
+    free_dev, pool_free = torch.cuda.mem_get_info(dev)[0], int(lib().hc_mempool_free_bytes())
+    if os.environ.get("HC_DEBUG_MEM") == "1":
+        import sys
+        sys.stderr.write("[ice_balance_csr] need %.2f GB, device free %.2f GB, pool free %.2f GB, torch reserved %.2f GB\n"
+                         % (need / 1e9, free_dev / 1e9, pool_free / 1e9, torch.cuda.memory_reserved(dev) / 1e9))
+    if free_dev + pool_free < need:
         torch.cuda.empty_cache()
     check(lib().hc_ice_csr_balance(ptr(csr.row_ptr), ptr(csr.col), ptr(csr.cnt), csr.row0, csr.nloc, ptr(d_prob),
                                    nprob, h_off, C.byref(params), ptr(bias), ptr(work), ptr(res), C.byref(info),

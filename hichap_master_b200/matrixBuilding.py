@@ -459,6 +459,12 @@ def two_step_device(T: DenseBatch, ti: int, M: DenseBatch, mi: int, P: DenseBatc
     host gap arrays."""
     n, dev = T.sizes[ti], T.device
     assert M.sizes[mi] == n and P.sizes[pi] == n
+    if M is P and pi == mi + 1 and n > 0:
+        # M and P next to each other in one batch: the batched driver (one launch per pass over both matrices, the gap
+        # decision read on the device -- no host round trip in the middle)
+        from .construction import _sub_batch
+        mats, gaps = kernels.twostep_batch(_sub_batch(T, ti, 1), _sub_batch(M, mi, 2))
+        return mats[0], mats[1], gaps[0], gaps[1]
     tp, mp, pp = (b.buf.data_ptr() + 4 * b.offsets[i] for b, i in ((T, ti), (M, mi), (P, pi)))
     rs_t, _ = kernels.rowstats(tp, T.lds[ti], n, n, dev, want_nnz=False)
     rs_m, nz_m = kernels.rowstats(mp, M.lds[mi], n, n, dev)
