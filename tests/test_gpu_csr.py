@@ -346,3 +346,34 @@ def test_fused_emit_equals_unfused_building_blocks(K, cuda_device):
     uk, cnts = np.unique(key, return_counts=True)
     got = up.cpu().numpy()
     assert np.array_equal(got >> vb, uk) and np.array_equal(got & ((1 << vb) - 1), cnts)
+
+
+@pytest.mark.parametrize("n,pad,longrun", [(1, 0, 0), (31, 3, 0), (32, 0, 0), (33, 1, 40), (511, 0, 600), (512, 7, 0), (513, 0, 0),
+                                           (4095, 0, 0), (4096, 5, 5000), (4097, 0, 0), (8191, 2, 9000), (8193, 0, 0),
+                                           (100_003, 11, 30_000)])
+def test_entry_reduce_sizes_around_chunk_and_tile_edges(K, cuda_device, n, pad, longrun):
+    """ent_count / ent_emit at list lengths around the 32-entry, 512-entry (warp chunk) and 4096-entry (tile) edges, with padding
+    entries behind n_valid and one run longer than a tile; both count modes; the swapped list checked too."""
+    import torch
+    nb = 70_000
+    cb, vb = K.key_col_bits(nb), K.entry_cnt_bits(nb)
+    rng = np.random.default_rng(n + pad)
+    r = rng.integers(0, nb, n); c = np.minimum(r + rng.integers(0, 3, n), nb - 1)
+    if longrun:
+        m = min(longrun, n)
+        r[:m] = 123; c[:m] = 456
+    for unit in (True, False):
+        v = np.ones(n, np.int64) if unit else rng.integers(1, 50, n)
+        ent = np.concatenate([(((r << cb) | c) << vb) | v, np.full(pad, -1, np.int64)]).astype(np.int64)
+        t = torch.from_numpy(ent[rng.permutation(ent.size)].copy()).to(cuda_device)
+        sent, _ = K.sort_entries(t, nb, vb, 2)
+        nv = torch.tensor([n], dtype=torch.int64, device=cuda_device)
+        up, lo, n_lo = K.reduce_entries(sent, nv, nb, unit=unit, want_lower=True)
+        key = (r << cb) | c
+        uk, inv = np.unique(key, return_inverse=True)
+        tot = np.bincount(inv, weights=v).astype(np.int64)
+        got = up.cpu().numpy()
+        assert np.array_equal(got >> vb, uk) and np.array_equal(got & ((1 << vb) - 1), tot), (n, unit)
+        ur, uc = uk >> cb, uk & ((1 << cb) - 1)
+        exp_lo = np.where(ur != uc, (((uc << cb) | ur) << vb) | tot, -1)
+        assert np.array_equal(lo.cpu().numpy(), exp_lo) and int(n_lo.item()) == int((ur != uc).sum())

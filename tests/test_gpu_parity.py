@@ -452,6 +452,14 @@ def test_two_step_sizes_vs_oracle(mb, n, seed):
     check_matrix(out[1], ref[1], "n=%d PM" % n)
     np.testing.assert_allclose(out[0], out[0].T, rtol=1e-12)   # symmetric
     np.testing.assert_allclose(out[0].mean(), mm.mean(), rtol=1e-9)  # rescaled to the raw mean
+    # M and P not next to each other in the batch: the per-matrix entry points (hc_twostep_alpha / hc_twostep_correct)
+    # instead of the batched driver
+    from hichap_master_b200.device import DenseBatch
+    b = DenseBatch.from_numpy([tm, mm, tm, pm])
+    nm, npm, gm, gp = mb.two_step_device(b, 0, b, 1, b, 3)
+    assert gaps_equal(gm, ref[2]) and gaps_equal(gp, ref[3])
+    check_matrix(nm.cpu().numpy(), ref[0], "n=%d MM (per-matrix path)" % n)
+    check_matrix(npm.cpu().numpy(), ref[1], "n=%d PM (per-matrix path)" % n)
 
 
 # ---------------------------------------------------------------------------------------
