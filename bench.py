@@ -225,7 +225,11 @@ def run_ours(args):
     sizes = [sizes_all[i] for i in mine]
 
     # ---- synthetic inputs, generated on the device, one seeded stream per chromosome ---------
-    sample_li = sorted(range(len(mine)), key=lambda li: sizes[li])[:2] if rank == 0 else []
+    # chromosomes the oracle re-computes from this run's pairs (rank 0): the two smallest -- and, on one GPU, the largest as
+    # well (chr1: ~15 s on one core), so that the single-core baseline is extrapolated from a cache-unfriendly chromosome
+    # too and the in-run parity check covers a full-size matrix
+    by_size = sorted(range(len(mine)), key=lambda li: sizes[li])
+    sample_li = (by_size[:2] + ([by_size[-1]] if world == 1 and len(by_size) > 2 and not args.no_cpu_baseline else [])) if rank == 0 else []
     sample = []
     cs, p1s, p2s = [], [], []
     for li, gi in enumerate(mine):
