@@ -496,7 +496,7 @@ def test_banded_binning_equals_direct_and_oracle(mb, cuda_device, n, res, mode):
         kernels.bin_pairs_local_banded(bad, res, DenseBatch(sizes, cuda_device))
 
 
-@pytest.mark.parametrize("csize,pile", [("8", False), ("4", True), ("16", False), ("2", True), ("1", True)])
+@pytest.mark.parametrize("csize,pile", [("8", False), ("4", True), ("16", False), ("2", True), ("1", True), ("1", False), ("0", True)])
 def test_cluster_binning_equals_direct(mb, cuda_device, monkeypatch, csize, pile):
     """HC_BIN_CLUSTER=N: the hottest diagonals are counted in the distributed shared memory of N-CTA clusters
     (16-bit counters, drained into the band when they reach 0x8000).  `pile`: 200 000 pairs in ONE cell, several
