@@ -584,8 +584,8 @@ def run_c4_section(args, world, rank, dev, peak, config="C4", standalone=False):
         return float(t.item())
 
     os.environ.setdefault("HC_ICE_TIME_KERNEL", "1")
-    out = {}
-    for rep in range(2):                       # rep 0 warms NCCL, allocator and caches
+    out, reps = {}, []
+    for rep in range(3):                       # rep 0 warms NCCL, allocator and caches; the faster of reps 1 and 2 is reported
         sync_all()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
@@ -606,7 +606,12 @@ def run_c4_section(args, world, rank, dev, peak, config="C4", standalone=False):
                    nnz_stored=float(nnz), nnz_max_rank=float(mx), encoding=st.get("encoding", "symmetric CSR, 8 B per stored entry"),
                    bytes_per_entry=float(st.get("bytes_per_entry", 8.0)), launches=int(st["launches"]),
                    pack_ms=maxr(st.get("pack_ms", 0.0)))
+        if rep:
+            reps.append(out)
         del csr
+    out = min(reps, key=lambda r: r["build_ms"] + r["ice_ms"])
+    out["repetitions"] = [{"binning_to_csr_ms": r["build_ms"], "ms_to_convergence": r["ice_ms"], "ice_loop_ms": r["loop_ms"],
+                           "ice_encode_ms": r["pack_ms"]} for r in reps]
     # the allreduce on its own (the in-loop one is issued by the library on the compute stream)
     ar_us = None
     if world > 1:
@@ -641,6 +646,8 @@ def run_c4_section(args, world, rank, dev, peak, config="C4", standalone=False):
         "nnz_imbalance": out["nnz_max_rank"] * world / out["nnz_stored"],
         "binning_to_csr_ms": out["build_ms"], "ms_to_convergence": out["ice_ms"], "ice_loop_ms": out["loop_ms"],
         "ice_encode_ms": out["pack_ms"],      # column-blocked re-encoding of the CSR (once per call), part of ms_to_convergence
+        "timing": "one warm-up repetition, then two timed ones (CUDA events, max over ranks); the faster one is reported, both are listed",
+        "repetitions": out["repetitions"],
         "iters": int(out["iters"]), "converged": bool(out["converged"]), "iter_ms": per_iter, "allreduce_us": ar_us,
         "gpu_launches": out["launches"], "encoding": out["encoding"],
         "roofline": {"bound": "hbm", "kernel": "CSR ICE iteration (stream kernel + update, allreduce included)", "unit": "GB/s",
