@@ -210,3 +210,34 @@ def test_cool_export_tables(tmp_path, small_genome_file):
         assert np.array_equal(R, np.triu(W))
     with pytest.raises(RuntimeError):
         cool_export.write_cool(path, small_genome_file, str(tmp_path / "x.mcool"))       # cooler is not installed here
+
+
+def test_entry_word_layout_invariants():
+    """Sort-path entries: (row << (cb + vb)) | (col << vb) | count must leave bit 63 clear (torch int64 / searchsorted on the
+    raw words), keep the padding key ~0 strictly above every real entry on the sorted bits, and the count field must hold
+    what the int32 CSR can hold (or less, with the overflow fallback)."""
+    from hichap_master_b200 import kernels
+    for nbins in (1, 2, 3, 255, 256, 257, 75_918, 303_641, 524_288, 607_271, 3_000_000, (1 << 24) - 1, 1 << 24):
+        cb, vb = kernels.key_col_bits(nbins), kernels.entry_cnt_bits(nbins)
+        assert (1 << cb) >= nbins and (cb == 1 or (1 << (cb - 1)) < nbins)
+        assert 1 <= vb <= 31 and 2 * cb + vb <= 63
+        top = (((nbins - 1) << cb | (nbins - 1)) << vb) | ((1 << vb) - 1)       # the largest real entry
+        assert 0 < top < (1 << 63)
+        # bits the sorts look at: two bin fields (+ the padding bit when nbins is a power of two)
+        nbits = kernels.key_sort_bits(nbins)
+        assert nbits == 2 * cb + (1 if nbins == (1 << cb) else 0) and vb + nbits <= 64
+        pad_key = ((1 << 64) - 1) >> vb & ((1 << nbits) - 1)
+        assert pad_key > (top >> vb)                                             # padding sorts strictly last
+        # swapping row and col keeps the word in range and is an involution
+        r, c, v = nbins - 1, 0, 5
+        e = ((r << cb | c) << vb) | v
+        sw = ((c << cb | r) << vb) | v
+        assert ((sw >> vb) & ((1 << cb) - 1)) == r and (sw >> (cb + vb)) == c and (e & ((1 << vb) - 1)) == (sw & ((1 << vb) - 1))
+
+
+def test_entry_count_bits_test_hook(monkeypatch):
+    from hichap_master_b200 import kernels
+    monkeypatch.setenv("HC_ENTRY_CNT_BITS", "6")
+    assert kernels.entry_cnt_bits(300) == 6
+    monkeypatch.setenv("HC_ENTRY_CNT_BITS", "40")
+    assert kernels.entry_cnt_bits(300) == 31          # never beyond what the layout leaves
