@@ -1114,8 +1114,10 @@ extern "C" int hc_ice_filter_bins(const double* nnz_marg, double* marg, int64_t 
                                                                       P->min_count, do_mad, bias);
     HC_LAUNCH_CHECK();
     if (do_mad) {
+        // small problems (one chromosome, a few thousand bins): the single-CTA kernel is one ~20 us launch, the grid-wide
+        // select ~20 launches of ~4 us each; HC_ICE_MAD_SINGLE=1 / 0 forces either
         const char* e_single = getenv("HC_ICE_MAD_SINGLE");
-        const bool single = e_single && atoi(e_single) != 0;
+        const bool single = e_single ? atoi(e_single) != 0 : nbins < 8192;
         if (single) {
             ice_filter_mad_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(marg, nbins, P->mad_max, bias, work);
             HC_LAUNCH_CHECK();
